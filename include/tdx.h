@@ -30,7 +30,7 @@ extern "C" {
 const char* tdx_last_error(void);
 /* Library + device probe: fills sm count, compute capability; fails if the device is not sm_100. */
 int tdx_device_info(int* sm_count, int* cc_major, int* cc_minor);
-/* sizeof() of the public structs (0: TdxOutSpec, 1: TdxIgemmDesc, ...) so bindings can verify their layout. */
+/* sizeof() of the public structs (0: TdxOutSpec, 1: TdxIgemmDesc, 2: TdxConvInDesc, 3: TdxConvOutDesc, 4: TdxEmbedBlock, 5: TdxEmbedDesc) so bindings can verify their layout. */
 int tdx_abi_sizeof(int which);
 
 /* ------------------------------------------------------------------------------------------------------------------
@@ -66,11 +66,11 @@ typedef struct TdxIgemmDesc {
   /* epilogue */
   int32_t epi_flags;       /* TDX_EPI_* */
   const float* cvec;       /* [n_img][c_out] fp32 embedding scale (TDX_EPI_EMB_SILU): v = mp_silu(v * c)          */
-  const void* resid;       /* bf16 NC8HW8 residual (TDX_EPI_RESID): v = clip(v + resid_scale * r', +-clip)       */
+  const void* resid;       /* bf16 NC8HW8 residual (TDX_EPI_RESID): v = v + resid_scale * r'                      */
   int32_t resid_spatial;   /* TDX_SP_SAME | TDX_SP_UP2 (r is H/2 x W/2) | TDX_SP_DOWN2 (r is 2H x 2W)            */
   int32_t resid_pnorm;     /* r' = pixelnorm(r) over channels (unet_block.py:121) when non-zero                  */
   float resid_scale;
-  float clip;
+  float clip;              /* > 0: v = clamp(v, -clip, +clip) after the residual (unet_block.py:153-154); 0: off  */
   TdxOutSpec out[3];
 } TdxIgemmDesc;
 
@@ -78,6 +78,112 @@ typedef struct TdxIgemmDesc {
 int64_t tdx_igemm_packed_weight_elems(const int32_t* a_channels, const int32_t* a_taps, int32_t n_seg, int32_t c_out);
 /* One launch of the persistent tcgen05 kernel. */
 int tdx_igemm_run(const TdxIgemmDesc* desc, void* stream);
+
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * First convolution (EDMUnet2D.forward, models/edm_unet.py:168-172: cat([x, ones]) -> enc['..._conv'] = MPConv 3x3).
+ * Reads the caller's planar NCHW input directly (up to two sources, e.g. the scaled noisy sample and the conditioning
+ * image of sample_decoder_diffusion_tiled, training/evaluation/sample_diffusion_decoder.py:108-110), appends the
+ * ones channel (zero-padded at the border like the reference's conv), and writes bf16 NC8HW8 outputs.
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct TdxConvInDesc {
+  const void* src[2];        /* NCHW planar, n_img x src_channels[i] x H x W */
+  int32_t src_channels[2];   /* channels of each source (second may be 0) */
+  int32_t src_dtype[2];      /* 0 = fp32, 1 = bf16 */
+  const float* src_scale[2]; /* optional DEVICE scalar multiplied into source i (precondition_inputs), or NULL */
+  const float* weight;       /* fp32 effective weights [c_out][sum(src_channels)+1][3][3] (ones channel last) */
+  int32_t c_out;             /* multiple of 32, <= 256 */
+  int32_t n_img, height, width;
+  TdxOutSpec out[3];         /* same semantics as TdxIgemmDesc.out (TDX_SP_SAME only) */
+} TdxConvInDesc;
+int tdx_conv_in_run(const TdxConvInDesc* desc, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Last convolution (out_conv with out_gain folded, models/edm_unet.py:179) + optionally the whole scheduler update
+ * (EDMDPMSolverMultistepScheduler.step, scheduler/dpmsolver.py:650-726, closed form of SURVEY.md Appendix B):
+ *     F  = conv3x3(x_raw)                          -> model_out (fp32 NCHW, optional)
+ *     x0 = c_skip*sample + c_out*F ; sample' = r*sample + (1-r)*x0 + k*(x0 - x0_prev) ; x0_prev = x0
+ * coef points at DEVICE floats {c_skip, c_out, r, k}.
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct TdxConvOutDesc {
+  const void* x;           /* bf16 NC8HW8, n_img x c_in x H x W */
+  int32_t c_in;            /* multiple of 8 */
+  const float* weight;     /* fp32 effective weights [c_out][c_in][3][3] */
+  int32_t c_out;           /* 1..8 */
+  int32_t n_img, height, width;
+  float* model_out;        /* fp32 NCHW [n_img][c_out][H][W] or NULL */
+  const float* sched_coef; /* DEVICE {c_skip, c_out, r, k} or NULL (no scheduler fusion) */
+  float* sample;           /* fp32 NCHW, updated in place (requires sched_coef) */
+  float* x0_prev;          /* fp32 NCHW solver history, read+written (requires sched_coef) */
+} TdxConvOutDesc;
+int tdx_conv_out_run(const TdxConvOutDesc* desc, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Embedding path (EDMUnet2D.compute_embeddings, models/edm_unet.py:145-159, + the per-block modulation vector of
+ * UNetBlock.forward, models/unet_block.py:129-131):
+ *     emb  = mp_silu(noise_linear(MPPositionalEmbedding(t)))        (or a caller-computed emb for conditional models)
+ *     c_b  = emb_linear_b(emb)*gain_b + 1 ;  c_b /= sqrt(mean(c_b^2) + 1e-8)          for every block b
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct TdxEmbedBlock {
+  const float* weight;   /* fp32 effective [c_out][emb_channels], emb_gain folded */
+  float* cvec;           /* fp32 [n_img][c_out] */
+  int32_t c_out;
+  int32_t _pad;
+} TdxEmbedBlock;
+typedef struct TdxEmbedDesc {
+  const float* noise_labels;   /* DEVICE fp32 [n_img] (trigflow t); used when emb_in is NULL */
+  const float* emb_in;         /* DEVICE fp32 [n_img][emb_channels] precomputed embedding, or NULL */
+  const float* noise_weight;   /* fp32 effective [emb_channels][noise_dims] */
+  const float* noise_freqs;    /* DEVICE fp32 [noise_dims/2]: the model's MPPositionalEmbedding.freqs buffer */
+  int32_t noise_dims;          /* even, <= 256 */
+  int32_t emb_channels;        /* <= 1024 */
+  int32_t n_img;
+  int32_t n_blocks;
+  const TdxEmbedBlock* blocks; /* HOST array of n_blocks entries (copied by the call) */
+} TdxEmbedDesc;
+int tdx_embed_run(const TdxEmbedDesc* desc, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Scheduler / consistency / blend elementwise kernels (fp32, vectorised).
+ * ------------------------------------------------------------------------------------------------------------------ */
+/* scheduler.step closed form on a standalone model output (dpmsolver.py:650-726); coef = host floats. */
+int tdx_sched_step(float* sample, const float* model_out, float* x0_prev, int64_t numel, float c_skip, float c_out,
+                   float r, float k, void* stream);
+/* canvas_val[c, y0+y, x0+x] += tile[c,y,x]*w[y,x] ; canvas_w[y0+y, x0+x] += w[y,x]   (sample_diffusion_decoder.py
+ * :122-123; infinite_tensor's window sum).  Separate rounding of the product and the sum (no FMA contraction), so
+ * applying tiles in the reference's row-major order reproduces its fp32 result bit for bit. */
+int tdx_blend_accumulate(float* canvas_val, float* canvas_w, int32_t channels, int32_t canvas_h, int32_t canvas_w_px,
+                         const float* tile, const float* window, int32_t tile_h, int32_t tile_w, int32_t y0,
+                         int32_t x0, void* stream);
+/* out = canvas_val / canvas_w [/ divisor]   (normalise-on-read, world_pipeline.py:1223,1301; the bounded samplers
+ * divide by sigma_data afterwards, sample_diffusion_decoder.py:211).  divisor == 1 skips the second division. */
+int tdx_blend_normalize(float* out, const float* canvas_val, const float* canvas_w, int32_t channels, int64_t plane,
+                        float divisor, void* stream);
+/* Tile-seeded N(0,1) field, bit-exact with inference/portable_rng.py + world_pipeline.py:66-115 */
+int tdx_noise_patch(uint64_t base_seed, int64_t y0, int64_t x0, int32_t h, int32_t w, int32_t channels,
+                    int32_t tile_h, int32_t tile_w, float* out, void* workspace, int64_t workspace_bytes,
+                    void* stream);
+int64_t tdx_noise_patch_workspace_bytes(int32_t channels, int32_t tile_h, int32_t tile_w);
+/* Synchronises `stream` and reports whether the last tdx_noise_patch on `workspace` completed its streams. */
+int tdx_noise_patch_status(void* workspace, void* stream);
+/* _tile_seed (world_pipeline.py:58-63): 64-bit seed of tile (ty, tx); host-side integer hash. */
+uint64_t tdx_tile_seed(uint64_t base_seed, int64_t ty, int64_t tx);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Program: a recorded sequence of the launches above with pre-built TMA descriptors, replayed as one CUDA graph.
+ * This is what EDMUnet2D.forward / the N-step tile sampler become: the Python host plans the launch list once per
+ * (model, batch, H, W) and then issues ONE call per forward (or per whole N-step solve).
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct TdxProgram TdxProgram;
+int tdx_program_create(TdxProgram** out);
+int tdx_program_add_conv_in(TdxProgram* p, const TdxConvInDesc* d);
+int tdx_program_add_igemm(TdxProgram* p, const TdxIgemmDesc* d);
+int tdx_program_add_conv_out(TdxProgram* p, const TdxConvOutDesc* d);
+int tdx_program_add_embed(TdxProgram* p, const TdxEmbedDesc* d);
+int tdx_program_num_launches(const TdxProgram* p);
+/* use_graph != 0: capture on first run, replay afterwards. */
+int tdx_program_run(TdxProgram* p, int use_graph, void* stream);
+int tdx_program_destroy(TdxProgram* p);
 
 #ifdef __cplusplus
 }

@@ -216,7 +216,8 @@ def compute_embeddings(sd, cfg, noise_labels, conditional_inputs):
 
 
 @torch.no_grad()
-def unet_forward(sd: dict, cfg: dict, x: torch.Tensor, noise_labels: torch.Tensor, conditional_inputs=None):
+def unet_forward(sd: dict, cfg: dict, x: torch.Tensor, noise_labels: torch.Tensor, conditional_inputs=None,
+                 trace: dict | None = None):
     """EDMUnet2D.forward, edm_unet.py:161-184 (return_logvar=False)."""
     enc, dec = block_plan(cfg)
     bk = cfg.get("block_kwargs") or {}
@@ -231,10 +232,14 @@ def unet_forward(sd: dict, cfg: dict, x: torch.Tensor, noise_labels: torch.Tenso
         else:
             x = unet_block(x, emb, sd, f"enc.{b['name']}.", b, **kw)
         skips.append(x)
+        if trace is not None:
+            trace[f"enc.{b['name']}."] = x
     for b in dec:
         if b.get("concat"):
             x = mp_concat([x, skips.pop()], float(cfg.get("concat_balance", 0.3)))
         x = unet_block(x, emb, sd, f"dec.{b['name']}.", b, **kw)
+        if trace is not None:
+            trace[f"dec.{b['name']}."] = x
     out_gain = sd["out_gain"] if "out_gain" in sd else 1.0
     return mp_conv(x, sd["out_conv.weight"], gain=out_gain)
 

@@ -27,6 +27,36 @@ class TdxIgemmDesc(C.Structure):
     ]
 
 
+class TdxConvInDesc(C.Structure):
+    _fields_ = [
+        ("src", C.c_void_p * 2), ("src_channels", C.c_int32 * 2), ("src_dtype", C.c_int32 * 2),
+        ("src_scale", C.c_void_p * 2), ("weight", C.c_void_p), ("c_out", C.c_int32), ("n_img", C.c_int32),
+        ("height", C.c_int32), ("width", C.c_int32), ("out", TdxOutSpec * 3),
+    ]
+
+
+class TdxConvOutDesc(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p), ("c_in", C.c_int32), ("weight", C.c_void_p), ("c_out", C.c_int32), ("n_img", C.c_int32),
+        ("height", C.c_int32), ("width", C.c_int32), ("model_out", C.c_void_p), ("sched_coef", C.c_void_p),
+        ("sample", C.c_void_p), ("x0_prev", C.c_void_p),
+    ]
+
+
+class TdxEmbedBlock(C.Structure):
+    _fields_ = [("weight", C.c_void_p), ("cvec", C.c_void_p), ("c_out", C.c_int32), ("_pad", C.c_int32)]
+
+
+class TdxEmbedDesc(C.Structure):
+    _fields_ = [
+        ("noise_labels", C.c_void_p), ("emb_in", C.c_void_p), ("noise_weight", C.c_void_p),
+        ("noise_freqs", C.c_void_p), ("noise_dims", C.c_int32), ("emb_channels", C.c_int32), ("n_img", C.c_int32),
+        ("n_blocks", C.c_int32), ("blocks", C.POINTER(TdxEmbedBlock)),
+    ]
+
+
+ABI_STRUCTS = [TdxOutSpec, TdxIgemmDesc, TdxConvInDesc, TdxConvOutDesc, TdxEmbedBlock, TdxEmbedDesc]
+
 OUT_NONE, OUT_RAW, OUT_SILU, OUT_PNORM_SILU = 0, 1, 2, 3
 SP_SAME, SP_DOWN2, SP_UP2 = 0, 1, 2
 EPI_EMB_SILU, EPI_RESID, EPI_PNORM = 1, 2, 4
@@ -55,14 +85,47 @@ def _declare(l: C.CDLL) -> None:
     l.tdx_igemm_packed_weight_elems.argtypes = [C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int32, C.c_int32]
     l.tdx_igemm_run.restype = C.c_int
     l.tdx_igemm_run.argtypes = [C.POINTER(TdxIgemmDesc), C.c_void_p]
-    for name, (res, args) in _OPTIONAL.items():
-        if hasattr(l, name):
-            fn = getattr(l, name)
-            fn.restype = res
-            fn.argtypes = args
-
-
-_OPTIONAL: dict = {}
+    l.tdx_abi_sizeof.restype = C.c_int
+    l.tdx_abi_sizeof.argtypes = [C.c_int]
+    for i, st in enumerate(ABI_STRUCTS):
+        if l.tdx_abi_sizeof(i) != C.sizeof(st):
+            raise TdxError(f"ABI mismatch for {st.__name__}: C {l.tdx_abi_sizeof(i)} vs ctypes {C.sizeof(st)}")
+    for name, desc in (("tdx_conv_in_run", TdxConvInDesc), ("tdx_conv_out_run", TdxConvOutDesc),
+                       ("tdx_embed_run", TdxEmbedDesc)):
+        fn = getattr(l, name)
+        fn.restype = C.c_int
+        fn.argtypes = [C.POINTER(desc), C.c_void_p]
+    l.tdx_sched_step.restype = C.c_int
+    l.tdx_sched_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_float, C.c_float,
+                                 C.c_float, C.c_void_p]
+    l.tdx_blend_accumulate.restype = C.c_int
+    l.tdx_blend_accumulate.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
+                                       C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
+    l.tdx_blend_normalize.restype = C.c_int
+    l.tdx_blend_normalize.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_float,
+                                      C.c_void_p]
+    l.tdx_noise_patch.restype = C.c_int
+    l.tdx_noise_patch.argtypes = [C.c_uint64, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                  C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+    l.tdx_noise_patch_workspace_bytes.restype = C.c_int64
+    l.tdx_noise_patch_workspace_bytes.argtypes = [C.c_int32, C.c_int32, C.c_int32]
+    l.tdx_noise_patch_status.restype = C.c_int
+    l.tdx_noise_patch_status.argtypes = [C.c_void_p, C.c_void_p]
+    l.tdx_tile_seed.restype = C.c_uint64
+    l.tdx_tile_seed.argtypes = [C.c_uint64, C.c_int64, C.c_int64]
+    l.tdx_program_create.restype = C.c_int
+    l.tdx_program_create.argtypes = [C.POINTER(C.c_void_p)]
+    for name, desc in (("tdx_program_add_conv_in", TdxConvInDesc), ("tdx_program_add_igemm", TdxIgemmDesc),
+                       ("tdx_program_add_conv_out", TdxConvOutDesc), ("tdx_program_add_embed", TdxEmbedDesc)):
+        fn = getattr(l, name)
+        fn.restype = C.c_int
+        fn.argtypes = [C.c_void_p, C.POINTER(desc)]
+    l.tdx_program_num_launches.restype = C.c_int
+    l.tdx_program_num_launches.argtypes = [C.c_void_p]
+    l.tdx_program_run.restype = C.c_int
+    l.tdx_program_run.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    l.tdx_program_destroy.restype = C.c_int
+    l.tdx_program_destroy.argtypes = [C.c_void_p]
 
 
 def check(rc: int) -> None:

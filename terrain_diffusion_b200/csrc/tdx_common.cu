@@ -90,6 +90,10 @@ extern "C" int tdx_abi_sizeof(int which) {
   switch (which) {
     case 0: return (int)sizeof(TdxOutSpec);
     case 1: return (int)sizeof(TdxIgemmDesc);
+    case 2: return (int)sizeof(TdxConvInDesc);
+    case 3: return (int)sizeof(TdxConvOutDesc);
+    case 4: return (int)sizeof(TdxEmbedBlock);
+    case 5: return (int)sizeof(TdxEmbedDesc);
     default: return -1;
   }
 }

@@ -1,0 +1,475 @@
+// CUDA-core kernels around the tensor-core path: first / last convolution (tiny K or tiny N), the embedding /
+// modulation vectors, and the fp32 elementwise scheduler + blend kernels.  All HBM-bound or launch-bound; the design
+// rules that matter are coalescing (threads walk x), 16-byte vectors on the NC8HW8 side and broadcast smem weights.
+#include "tdx_common.h"
+#include "tdx_ptx.cuh"
+
+namespace tdx {
+
+__device__ __forceinline__ float mp_silu_precise(float x) { return x / (1.0f + expf(-x)) / 0.596f; }
+
+// ------------------------------------------------------------------------------------------------ first conv
+struct ConvInParams {
+  const void* src[2];
+  int src_ch[2];
+  int src_dtype[2];
+  const float* src_scale[2];
+  const float* weight;
+  int ci;  // total input channels incl. the ones channel
+  int cout;
+  int H, W;
+  TdxOutSpec out[3];
+};
+
+__device__ __forceinline__ float load_in(const void* base, int dtype, size_t idx) {
+  if (dtype == 0) return __ldg(reinterpret_cast<const float*>(base) + idx);
+  return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(base)[idx]);
+}
+
+__global__ void __launch_bounds__(128) conv_in_kernel(const ConvInParams p) {
+  extern __shared__ float ws[];  // [tap][ci][cout]
+  const int CI = p.ci, CO = p.cout;
+  for (int i = threadIdx.x; i < 9 * CI * CO; i += blockDim.x) {
+    const int oc = i % CO, ci = (i / CO) % CI, tap = i / (CO * CI);
+    ws[i] = p.weight[(oc * CI + ci) * 9 + tap];
+  }
+  __syncthreads();
+  const int img = blockIdx.y;
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= p.H * p.W) return;
+  const int y = pix / p.W, x = pix % p.W;
+  const size_t plane = (size_t)p.H * p.W;
+  const float s0 = p.src_scale[0] ? __ldg(p.src_scale[0]) : 1.0f;
+  const float s1 = p.src_scale[1] ? __ldg(p.src_scale[1]) : 1.0f;
+  const int c0n = p.src_ch[0], c1n = p.src_ch[1];
+  const int C8 = CO >> 3;
+  float sumsq = 0.f;
+  bool want_pnorm = false;
+  const uint4* raw_ptr = nullptr;
+#pragma unroll
+  for (int o = 0; o < 3; ++o) {
+    if (p.out[o].kind == TDX_OUT_PNORM_SILU) want_pnorm = true;
+    if (p.out[o].kind == TDX_OUT_RAW) raw_ptr = reinterpret_cast<const uint4*>(p.out[o].ptr);
+  }
+
+  for (int oc0 = 0; oc0 < CO; oc0 += 32) {
+    float acc[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+    for (int tap = 0; tap < 9; ++tap) {
+      const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
+      if (yy < 0 || yy >= p.H || xx < 0 || xx >= p.W) continue;  // zero padding (also of the ones channel)
+      const size_t off = (size_t)yy * p.W + xx;
+      for (int ci = 0; ci < CI; ++ci) {
+        float v;
+        if (ci < c0n) v = load_in(p.src[0], p.src_dtype[0], ((size_t)img * c0n + ci) * plane + off) * s0;
+        else if (ci < c0n + c1n) v = load_in(p.src[1], p.src_dtype[1], ((size_t)img * c1n + (ci - c0n)) * plane + off) * s1;
+        else v = 1.0f;
+        const float4* w4 = reinterpret_cast<const float4*>(ws + (tap * CI + ci) * CO + oc0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 w = w4[j];
+          acc[4 * j + 0] = fmaf(w.x, v, acc[4 * j + 0]);
+          acc[4 * j + 1] = fmaf(w.y, v, acc[4 * j + 1]);
+          acc[4 * j + 2] = fmaf(w.z, v, acc[4 * j + 2]);
+          acc[4 * j + 3] = fmaf(w.w, v, acc[4 * j + 3]);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) sumsq = fmaf(acc[j], acc[j], sumsq);
+#pragma unroll
+    for (int o = 0; o < 3; ++o) {
+      const TdxOutSpec& os = p.out[o];
+      if (os.kind != TDX_OUT_RAW && os.kind != TDX_OUT_SILU) continue;
+      uint4* optr = reinterpret_cast<uint4*>(os.ptr) + ((size_t)img * C8 + (oc0 >> 3)) * plane + pix;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        float w[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float t = acc[g * 8 + i];
+          w[i] = os.kind == TDX_OUT_RAW ? t : mp_silu_f(t * os.scale);
+        }
+        uint4 u;
+        u.x = pack_bf16x2(w[0], w[1]); u.y = pack_bf16x2(w[2], w[3]);
+        u.z = pack_bf16x2(w[4], w[5]); u.w = pack_bf16x2(w[6], w[7]);
+        optr[(size_t)g * plane] = u;
+      }
+    }
+  }
+  if (want_pnorm) {
+    // second pass over this thread's own raw output (bf16) -- the raw output is always requested alongside
+    const float inv = 1.0f / (1e-4f + sqrtf(sumsq / (float)CO));
+#pragma unroll
+    for (int o = 0; o < 3; ++o) {
+      const TdxOutSpec& os = p.out[o];
+      if (os.kind != TDX_OUT_PNORM_SILU) continue;
+      for (int g = 0; g < C8; ++g) {
+        const uint4 u = raw_ptr[((size_t)img * C8 + g) * plane + pix];
+        float a[8];
+        unpack_bf16x2(u.x, a[0], a[1]); unpack_bf16x2(u.y, a[2], a[3]);
+        unpack_bf16x2(u.z, a[4], a[5]); unpack_bf16x2(u.w, a[6], a[7]);
+        uint4 r;
+        r.x = pack_bf16x2(mp_silu_f(a[0] * inv), mp_silu_f(a[1] * inv));
+        r.y = pack_bf16x2(mp_silu_f(a[2] * inv), mp_silu_f(a[3] * inv));
+        r.z = pack_bf16x2(mp_silu_f(a[4] * inv), mp_silu_f(a[5] * inv));
+        r.w = pack_bf16x2(mp_silu_f(a[6] * inv), mp_silu_f(a[7] * inv));
+        reinterpret_cast<uint4*>(os.ptr)[((size_t)img * C8 + g) * plane + pix] = r;
+      }
+    }
+  }
+}
+
+int direct_prepare();
+
+int conv_in_validate(const TdxConvInDesc& d) {
+  TDX_REQUIRE(d.src[0] && d.src_channels[0] > 0, "conv_in: src[0] missing");
+  TDX_REQUIRE(d.src_channels[1] == 0 || d.src[1], "conv_in: src[1] missing");
+  TDX_REQUIRE(d.weight, "conv_in: weight is null");
+  TDX_REQUIRE(d.c_out >= 32 && d.c_out <= 256 && d.c_out % 32 == 0, "conv_in: c_out=%d", d.c_out);
+  TDX_REQUIRE(d.n_img >= 1 && d.height >= 1 && d.width >= 1, "conv_in: bad shape");
+  const int ci = d.src_channels[0] + d.src_channels[1] + 1;
+  TDX_REQUIRE(9 * ci * d.c_out * 4 <= 200 * 1024, "conv_in: weights (%d in, %d out) exceed shared memory", ci, d.c_out);
+  bool has_raw = false, has_pn = false;
+  for (int o = 0; o < 3; ++o) {
+    if (d.out[o].kind == TDX_OUT_NONE) continue;
+    TDX_REQUIRE(d.out[o].ptr, "conv_in: out[%d].ptr is null", o);
+    TDX_REQUIRE(d.out[o].spatial == TDX_SP_SAME, "conv_in: only TDX_SP_SAME outputs");
+    has_raw |= d.out[o].kind == TDX_OUT_RAW;
+    has_pn |= d.out[o].kind == TDX_OUT_PNORM_SILU;
+  }
+  TDX_REQUIRE(!has_pn || has_raw, "conv_in: a PNORM_SILU output needs a RAW output too");
+  return TDX_OK;
+}
+
+int conv_in_launch(const TdxConvInDesc& d, cudaStream_t stream) {
+  ConvInParams p;
+  for (int i = 0; i < 2; ++i) {
+    p.src[i] = d.src[i];
+    p.src_ch[i] = d.src_channels[i];
+    p.src_dtype[i] = d.src_dtype[i];
+    p.src_scale[i] = d.src_scale[i];
+  }
+  p.weight = d.weight;
+  p.ci = d.src_channels[0] + d.src_channels[1] + 1;
+  p.cout = d.c_out;
+  p.H = d.height;
+  p.W = d.width;
+  for (int o = 0; o < 3; ++o) p.out[o] = d.out[o];
+  const int smem = 9 * p.ci * p.cout * 4;
+  int rc_prep = direct_prepare();
+  if (rc_prep != TDX_OK) return rc_prep;
+  dim3 grid((d.height * d.width + 127) / 128, d.n_img);
+  conv_in_kernel<<<grid, 128, smem, stream>>>(p);
+  TDX_CHECK_CUDA(cudaGetLastError());
+  return TDX_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ last conv (+ scheduler)
+struct ConvOutParams {
+  const uint4* x;
+  int C8, cout, H, W;
+  const float* weight;
+  float* model_out;
+  const float* coef;
+  float* sample;
+  float* x0_prev;
+};
+
+// One DPM-Solver++(2M) update in the EDM closed form (scheduler/dpmsolver.py:419-561).
+__device__ __forceinline__ void sched_update(float x, float f, float x0p, float c_skip, float c_out, float r, float k,
+                                             float& x_new, float& x0) {
+  x0 = __fadd_rn(__fmul_rn(c_skip, x), __fmul_rn(c_out, f));
+  float t = __fadd_rn(__fmul_rn(r, x), __fmul_rn(1.0f - r, x0));
+  x_new = __fadd_rn(t, __fmul_rn(k, __fsub_rn(x0, x0p)));
+}
+
+__global__ void __launch_bounds__(128) conv_out_kernel(const ConvOutParams p) {
+  extern __shared__ float ws[];  // [tap][c][8]
+  const int C = p.C8 * 8;
+  for (int i = threadIdx.x; i < 9 * C * 8; i += blockDim.x) {
+    const int oc = i & 7, c = (i >> 3) % C, tap = i / (8 * C);
+    ws[i] = oc < p.cout ? p.weight[(oc * C + c) * 9 + tap] : 0.f;
+  }
+  __syncthreads();
+  const int img = blockIdx.y;
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= p.H * p.W) return;
+  const int y = pix / p.W, x = pix % p.W;
+  const size_t plane = (size_t)p.H * p.W;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  for (int tap = 0; tap < 9; ++tap) {
+    const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
+    if (yy < 0 || yy >= p.H || xx < 0 || xx >= p.W) continue;
+    const uint4* src = p.x + (size_t)img * p.C8 * plane + (size_t)yy * p.W + xx;
+    for (int g = 0; g < p.C8; ++g) {
+      const uint4 u = __ldg(src + (size_t)g * plane);
+      float a[8];
+      unpack_bf16x2(u.x, a[0], a[1]); unpack_bf16x2(u.y, a[2], a[3]);
+      unpack_bf16x2(u.z, a[4], a[5]); unpack_bf16x2(u.w, a[6], a[7]);
+      const float4* w4 = reinterpret_cast<const float4*>(ws + (tap * C + g * 8) * 8);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float4 wa = w4[2 * e], wb = w4[2 * e + 1];
+        acc[0] = fmaf(wa.x, a[e], acc[0]); acc[1] = fmaf(wa.y, a[e], acc[1]);
+        acc[2] = fmaf(wa.z, a[e], acc[2]); acc[3] = fmaf(wa.w, a[e], acc[3]);
+        acc[4] = fmaf(wb.x, a[e], acc[4]); acc[5] = fmaf(wb.y, a[e], acc[5]);
+        acc[6] = fmaf(wb.z, a[e], acc[6]); acc[7] = fmaf(wb.w, a[e], acc[7]);
+      }
+    }
+  }
+  float cs = 0.f, co = 0.f, r = 0.f, k = 0.f;
+  if (p.coef) { cs = __ldg(p.coef); co = __ldg(p.coef + 1); r = __ldg(p.coef + 2); k = __ldg(p.coef + 3); }
+#pragma unroll
+  for (int oc = 0; oc < 8; ++oc) {
+    if (oc >= p.cout) break;
+    const size_t idx = ((size_t)img * p.cout + oc) * plane + pix;
+    if (p.model_out) p.model_out[idx] = acc[oc];
+    if (p.coef) {
+      float xn, x0;
+      sched_update(p.sample[idx], acc[oc], p.x0_prev[idx], cs, co, r, k, xn, x0);
+      p.sample[idx] = xn;
+      p.x0_prev[idx] = x0;
+    }
+  }
+}
+
+// Opt in to > 48 KB dynamic shared memory once (must not happen inside a stream capture).
+int direct_prepare() {
+  static bool done = false;
+  if (!done) {
+    TDX_CHECK_CUDA(cudaFuncSetAttribute(conv_in_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    TDX_CHECK_CUDA(cudaFuncSetAttribute(conv_out_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    done = true;
+  }
+  return TDX_OK;
+}
+
+int conv_out_validate(const TdxConvOutDesc& d) {
+  TDX_REQUIRE(d.x && d.weight, "conv_out: null x / weight");
+  TDX_REQUIRE(d.c_in > 0 && d.c_in % 8 == 0, "conv_out: c_in=%d not a multiple of 8", d.c_in);
+  TDX_REQUIRE(d.c_out >= 1 && d.c_out <= 8, "conv_out: c_out=%d not in 1..8", d.c_out);
+  TDX_REQUIRE(9 * d.c_in * 8 * 4 <= 200 * 1024, "conv_out: c_in=%d too large", d.c_in);
+  TDX_REQUIRE(d.model_out || d.sched_coef, "conv_out: nothing to write");
+  if (d.sched_coef) TDX_REQUIRE(d.sample && d.x0_prev, "conv_out: scheduler fusion needs sample and x0_prev");
+  return TDX_OK;
+}
+
+int conv_out_launch(const TdxConvOutDesc& d, cudaStream_t stream) {
+  ConvOutParams p;
+  p.x = reinterpret_cast<const uint4*>(d.x);
+  p.C8 = d.c_in / 8;
+  p.cout = d.c_out;
+  p.H = d.height;
+  p.W = d.width;
+  p.weight = d.weight;
+  p.model_out = d.model_out;
+  p.coef = d.sched_coef;
+  p.sample = d.sample;
+  p.x0_prev = d.x0_prev;
+  const int smem = 9 * d.c_in * 8 * 4;
+  int rc_prep = direct_prepare();
+  if (rc_prep != TDX_OK) return rc_prep;
+  dim3 grid((d.height * d.width + 127) / 128, d.n_img);
+  conv_out_kernel<<<grid, 128, smem, stream>>>(p);
+  TDX_CHECK_CUDA(cudaGetLastError());
+  return TDX_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ embedding vectors
+constexpr int kMaxEmbedBlocks = 64;
+struct EmbedParams {
+  const float* labels;
+  const float* emb_in;
+  const float* noise_weight;
+  const float* noise_freqs;
+  int noise_dims, E;
+  TdxEmbedBlock blocks[kMaxEmbedBlocks];
+};
+
+__global__ void __launch_bounds__(256) embed_kernel(const __grid_constant__ EmbedParams p) {
+  __shared__ float pe[256];
+  __shared__ float emb[1024];
+  __shared__ float cval[256];
+  __shared__ float red[8];
+  const int b = blockIdx.x, img = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (p.emb_in) {
+    for (int j = threadIdx.x; j < p.E; j += blockDim.x) emb[j] = p.emb_in[(size_t)img * p.E + j];
+  } else {
+    // MPPositionalEmbedding (mp_layers.py:88-107), fp32
+    const int half = p.noise_dims >> 1;
+    const float t = p.labels[img];
+    for (int i = threadIdx.x; i < half; i += blockDim.x) {
+      const float yv = t * p.noise_freqs[i];
+      pe[i] = sinf(yv) * 1.41421356237309515f;
+      pe[half + i] = cosf(yv) * 1.41421356237309515f;
+    }
+    __syncthreads();
+    for (int j = warp; j < p.E; j += 8) {
+      const float* wr = p.noise_weight + (size_t)j * p.noise_dims;
+      float s = 0.f;
+      for (int i = lane; i < p.noise_dims; i += 32) s = fmaf(wr[i], pe[i], s);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffff, s, o);
+      if (lane == 0) emb[j] = mp_silu_precise(s);  // mp_sum of a single embed with weight [1] is the identity
+    }
+  }
+  __syncthreads();
+  const TdxEmbedBlock& blk = p.blocks[b];
+  float local_sq = 0.f;
+  for (int n = warp; n < blk.c_out; n += 8) {
+    const float* wr = blk.weight + (size_t)n * p.E;
+    float s = 0.f;
+    for (int j = lane; j < p.E; j += 32) s = fmaf(wr[j], emb[j], s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffff, s, o);
+    s += 1.0f;
+    if (lane == 0) cval[n] = s;
+    local_sq += s * s;  // identical in all lanes
+  }
+  if (lane == 0) red[warp] = local_sq;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) tot += red[w];
+  const float inv = rsqrtf(tot / (float)blk.c_out + 1e-8f);
+  for (int n = threadIdx.x; n < blk.c_out; n += blockDim.x) blk.cvec[(size_t)img * blk.c_out + n] = cval[n] * inv;
+}
+
+int embed_validate(const TdxEmbedDesc& d) {
+  TDX_REQUIRE(d.n_blocks >= 1 && d.n_blocks <= kMaxEmbedBlocks, "embed: n_blocks=%d not in 1..%d", d.n_blocks,
+              kMaxEmbedBlocks);
+  TDX_REQUIRE(d.blocks, "embed: blocks is null");
+  TDX_REQUIRE(d.emb_channels >= 1 && d.emb_channels <= 1024, "embed: emb_channels=%d", d.emb_channels);
+  TDX_REQUIRE(d.n_img >= 1, "embed: n_img");
+  if (!d.emb_in) {
+    TDX_REQUIRE(d.noise_labels && d.noise_weight && d.noise_freqs, "embed: noise path needs labels, weight, freqs");
+    TDX_REQUIRE(d.noise_dims >= 2 && d.noise_dims <= 256 && d.noise_dims % 2 == 0, "embed: noise_dims=%d",
+                d.noise_dims);
+  }
+  for (int b = 0; b < d.n_blocks; ++b)
+    TDX_REQUIRE(d.blocks[b].weight && d.blocks[b].cvec && d.blocks[b].c_out >= 1 && d.blocks[b].c_out <= 256,
+                "embed: block %d invalid", b);
+  return TDX_OK;
+}
+
+int embed_launch(const TdxEmbedDesc& d, cudaStream_t stream) {
+  EmbedParams p;
+  memset(&p, 0, sizeof(p));
+  p.labels = d.noise_labels;
+  p.emb_in = d.emb_in;
+  p.noise_weight = d.noise_weight;
+  p.noise_freqs = d.noise_freqs;
+  p.noise_dims = d.noise_dims;
+  p.E = d.emb_channels;
+  for (int b = 0; b < d.n_blocks; ++b) p.blocks[b] = d.blocks[b];
+  dim3 grid(d.n_blocks, d.n_img);
+  embed_kernel<<<grid, 256, 0, stream>>>(p);
+  TDX_CHECK_CUDA(cudaGetLastError());
+  return TDX_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ elementwise fp32
+__global__ void sched_step_kernel(float* sample, const float* f, float* x0_prev, int64_t n, float cs, float co, float r,
+                                  float k) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    float xn, x0;
+    sched_update(sample[i], f[i], x0_prev[i], cs, co, r, k, xn, x0);
+    sample[i] = xn;
+    x0_prev[i] = x0;
+  }
+}
+
+__global__ void blend_accumulate_kernel(float* cval, float* cw, int channels, int CH, int CW, const float* tile,
+                                        const float* window, int th, int tw, int y0, int x0) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y;
+  if (x >= tw) return;
+  const int Y = y0 + y, X = x0 + x;
+  if (Y < 0 || Y >= CH || X < 0 || X >= CW) return;
+  const float w = window[(size_t)y * tw + x];
+  const size_t cidx = (size_t)Y * CW + X;
+  for (int c = 0; c < channels; ++c) {
+    const float v = __fmul_rn(tile[((size_t)c * th + y) * tw + x], w);
+    cval[(size_t)c * CH * CW + cidx] = __fadd_rn(cval[(size_t)c * CH * CW + cidx], v);
+  }
+  cw[cidx] = __fadd_rn(cw[cidx], w);
+}
+
+__global__ void blend_normalize_kernel(float* out, const float* cval, const float* cw, int channels, int64_t plane,
+                                       float divisor) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t n = plane * channels;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    const float q = __fdiv_rn(cval[i], cw[i % plane]);
+    out[i] = divisor == 1.0f ? q : __fdiv_rn(q, divisor);
+  }
+}
+
+}  // namespace tdx
+
+using namespace tdx;
+
+extern "C" int tdx_conv_in_run(const TdxConvInDesc* d, void* stream) {
+  if (!d) { set_error("conv_in: null descriptor"); return TDX_E_INVALID; }
+  int rc = conv_in_validate(*d);
+  if (rc != TDX_OK) return rc;
+  return conv_in_launch(*d, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int tdx_conv_out_run(const TdxConvOutDesc* d, void* stream) {
+  if (!d) { set_error("conv_out: null descriptor"); return TDX_E_INVALID; }
+  int rc = conv_out_validate(*d);
+  if (rc != TDX_OK) return rc;
+  return conv_out_launch(*d, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int tdx_embed_run(const TdxEmbedDesc* d, void* stream) {
+  if (!d) { set_error("embed: null descriptor"); return TDX_E_INVALID; }
+  int rc = embed_validate(*d);
+  if (rc != TDX_OK) return rc;
+  return embed_launch(*d, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int tdx_sched_step(float* sample, const float* model_out, float* x0_prev, int64_t numel, float c_skip,
+                              float c_out, float r, float k, void* stream) {
+  TDX_REQUIRE(sample && model_out && x0_prev && numel > 0, "sched_step: bad arguments");
+  int blocks = (int)((numel + 255) / 256);
+  if (blocks > sm_count() * 8) blocks = sm_count() * 8;
+  sched_step_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(sample, model_out, x0_prev, numel,
+                                                                               c_skip, c_out, r, k);
+  TDX_CHECK_CUDA(cudaGetLastError());
+  return TDX_OK;
+}
+
+extern "C" int tdx_blend_accumulate(float* canvas_val, float* canvas_w, int32_t channels, int32_t canvas_h,
+                                    int32_t canvas_w_px, const float* tile, const float* window, int32_t tile_h,
+                                    int32_t tile_w, int32_t y0, int32_t x0, void* stream) {
+  TDX_REQUIRE(canvas_val && canvas_w && tile && window, "blend_accumulate: null pointer");
+  TDX_REQUIRE(channels >= 1 && tile_h >= 1 && tile_w >= 1 && canvas_h >= 1 && canvas_w_px >= 1,
+              "blend_accumulate: bad shape");
+  dim3 grid((tile_w + 127) / 128, tile_h);
+  blend_accumulate_kernel<<<grid, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      canvas_val, canvas_w, channels, canvas_h, canvas_w_px, tile, window, tile_h, tile_w, y0, x0);
+  TDX_CHECK_CUDA(cudaGetLastError());
+  return TDX_OK;
+}
+
+extern "C" int tdx_blend_normalize(float* out, const float* canvas_val, const float* canvas_w, int32_t channels,
+                                   int64_t plane, float divisor, void* stream) {
+  TDX_REQUIRE(out && canvas_val && canvas_w && channels >= 1 && plane >= 1, "blend_normalize: bad arguments");
+  int64_t n = plane * channels;
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > sm_count() * 8) blocks = sm_count() * 8;
+  blend_normalize_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(out, canvas_val, canvas_w,
+                                                                                    channels, plane, divisor);
+  TDX_CHECK_CUDA(cudaGetLastError());
+  return TDX_OK;
+}

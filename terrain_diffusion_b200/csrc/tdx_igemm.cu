@@ -265,11 +265,12 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CU
               unpack_bf16x2(u.z, rr[4], rr[5]);
               unpack_bf16x2(u.w, rr[6], rr[7]);
 #pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                float t = fmaf(rscale, rr[i], v[g * 8 + i]);
-                v[g * 8 + i] = fminf(fmaxf(t, -p.clip), p.clip);
-              }
+              for (int i = 0; i < 8; ++i) v[g * 8 + i] = fmaf(rscale, rr[i], v[g * 8 + i]);
             }
+          }
+          if (p.clip > 0.f) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = fminf(fmaxf(v[i], -p.clip), p.clip);
           }
           if (need_norm && !last) {
 #pragma unroll
@@ -347,6 +348,15 @@ static int smem_layout(int cout, int* SB_out) {
   return bytes;
 }
 
+int igemm_prepare() {
+  static bool attr_set = false;
+  if (!attr_set) {
+    TDX_CHECK_CUDA(cudaFuncSetAttribute(igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+    attr_set = true;
+  }
+  return TDX_OK;
+}
+
 int igemm_launch(const TdxIgemmDesc& d, const CUtensorMap* tms, cudaStream_t stream) {
   IgemmParams p;
   memset(&p, 0, sizeof(p));
@@ -376,11 +386,8 @@ int igemm_launch(const TdxIgemmDesc& d, const CUtensorMap* tms, cudaStream_t str
   p.clip = d.clip;
   for (int o = 0; o < 3; ++o) p.out[o] = d.out[o];
 
-  static bool attr_set = false;
-  if (!attr_set) {
-    TDX_CHECK_CUDA(cudaFuncSetAttribute(igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
-    attr_set = true;
-  }
+  int rc_prep = igemm_prepare();
+  if (rc_prep != TDX_OK) return rc_prep;
   int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
   const CUtensorMap& t0 = tms[0];
   const CUtensorMap& t1 = tms[d.n_seg > 1 ? 1 : 0];

@@ -1,0 +1,55 @@
+"""Whole N-step tile solves as ONE CUDA graph.
+
+The reference's per-tile loop (training/evaluation/sample_diffusion_decoder.py:105-120; world_pipeline.py:934-949)
+runs, per step: precondition_inputs, trigflow_precondition_noise, cat, the U-Net, scheduler.step -- thousands of
+launches and host-side scalar math.  Here the step sequence is planned once: the scaled-sample/cond concat is folded
+into the first convolution, scheduler.step into the last one, and the per-step scalars (c_in, t, c_skip, c_out, r, k)
+sit in a small device table, so a K-step solve of a batch of tiles is a single graph launch of ~80*K kernels.
+"""
+from __future__ import annotations
+
+import torch
+
+from ..models.plan import UNetEmitter, UNetProgram
+
+
+class DiffusionSolve:
+    """K-step EDM DPM-Solver++ solve of `n` independent tiles: sample[n, Cs, h, w] (<- noise*sigma0), cond[n, Cc, h, w]."""
+
+    def __init__(self, model, scheduler, n: int, h: int, w: int, num_steps: int):
+        fw = model.folded()
+        dev = fw.device
+        self.model, self.n, self.h, self.w, self.num_steps = model, n, h, w, num_steps
+        cs = fw.out_channels
+        cc = fw.in_channels - cs
+        scheduler.set_timesteps(num_steps)
+        order = scheduler.order_schedule()
+        co = [scheduler.step_coefficients(i, order[i]) for i in range(num_steps)]
+        self.coef = torch.tensor([[c["c_skip"], c["c_out"], c["r"], c["k"]] for c in co], dtype=torch.float64).to(
+            torch.float32).to(dev).contiguous()
+        self.c_in = torch.tensor([c["c_in"] for c in co], dtype=torch.float64).to(torch.float32).to(dev).contiguous()
+        self.labels = torch.tensor([[c["t"]] * n for c in co], dtype=torch.float64).to(torch.float32).to(
+            dev).contiguous()
+        self.sample = torch.zeros((n, cs, h, w), dtype=torch.float32, device=dev)
+        self.cond = torch.zeros((n, max(cc, 1), h, w), dtype=torch.float32, device=dev)
+        self.x0_prev = torch.zeros_like(self.sample)
+        self.prog = UNetProgram()
+        em = UNetEmitter(fw, n, h, w)
+        for i in range(num_steps):
+            srcs = [(self.sample, cs, self.c_in[i:i + 1])]
+            if cc > 0:
+                srcs.append((self.cond, cc, None))
+            em.emit(self.prog, srcs, labels=self.labels[i], model_out=None,
+                    sched=dict(coef=self.coef[i], sample=self.sample, x0_prev=self.x0_prev))
+        self.launches_per_solve = self.prog.n_launch
+
+    @torch.no_grad()
+    def run(self, noise: torch.Tensor, cond: torch.Tensor | None, use_graph: bool = True) -> torch.Tensor:
+        """noise: [n, Cs, h, w] initial sample (already scaled by sigma_0); returns the denoised sample (a view of the
+        solver's state buffer -- copy it before the next run)."""
+        self.sample.copy_(noise)
+        if cond is not None:
+            self.cond.copy_(cond)
+        self.x0_prev.zero_()
+        self.prog.run(use_graph)
+        return self.sample

@@ -1,0 +1,419 @@
+"""Launch planner: turns an EDMUnet2D (reference: terrain_diffusion/models/edm_unet.py:67-184) into a libtdx Program.
+
+The reference evaluates ~6 500 ATen ops per forward (weight re-normalisation, pixel-norm, mp_silu, mp_sum, mp_concat,
+resample, clip around 96 convolutions).  Here every UNetBlock (models/unet_block.py:116-156) becomes two launches of the
+tcgen05 implicit-GEMM kernel (three for encoder blocks with a 1x1 skip) whose epilogues carry all of that:
+
+  enc block   [K1: 1x1 skip -> pixel-norm -> (x_n, mp_silu(x_n))]                         (only if Cin != Cout)
+              res0: conv3x3(a) -> mp_silu(y * c)                                          (c = embedding modulation)
+              res1: conv3x3(h)*t/n + (1-t)/n * pixelnorm(x) -> clip -> outputs
+  dec block   res0: conv3x3 over K-slabs [mp_silu(s1*x) | mp_silu(s2*skip)] -> mp_silu(y * c)
+              res1: one GEMM over K-slabs [h (3x3) | x (1x1 skip) | skip (1x1 skip)] with mp_sum / mp_concat constants
+                    folded into the weights -> clip -> outputs          (or residual add when there is no skip conv)
+
+"outputs" = what the consumers need, written by the producer's epilogue: the raw block output (skip connection /
+residual / 1x1 K-slab), the next block's activated input (mp_silu, or pixel-norm + mp_silu, optionally stride-2
+sub-sampled or nearest-x2 up-sampled) and the decoder-side activated skip.  Weights are normalised/folded ONCE here
+(the reference redoes it every forward, mp_layers.py:203-213).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from .. import _lib as L
+from ..layout import pack_weight_segments
+
+
+def effective_weight(w: torch.Tensor, gain=1.0) -> torch.Tensor:
+    """fp32 weight MPConv.forward convolves with (mp_layers.py:203-213): global-RMS normalise, gain / sqrt(fan_in)."""
+    w = w.detach().to(torch.float32)
+    norm = torch.linalg.vector_norm(w)
+    norm = torch.add(1e-4, norm, alpha=np.sqrt(1.0 / w.numel()))
+    w = w / norm
+    if isinstance(gain, torch.Tensor):
+        gain = gain.detach().to(torch.float32)
+    return w * (gain / np.sqrt(w[0].numel()))
+
+
+def mp_concat_scales(n_a: int, n_b: int, t: float) -> tuple[float, float]:
+    """Per-tensor scalars of mp_concat (mp_layers.py:65-86)."""
+    c = math.sqrt((n_a + n_b) / ((1 - t) ** 2 + t ** 2))
+    return c / math.sqrt(n_a) * (1 - t), c / math.sqrt(n_b) * t
+
+
+def block_plan(cfg: dict) -> tuple[list, list]:
+    """Module order / shapes of EDMUnet2D.__init__ (edm_unet.py:105-137)."""
+    mults = cfg.get("model_channel_mults") or [1, 2, 3, 4]
+    mc = cfg.get("model_channels", 128)
+    lpb = cfg.get("layers_per_block", 2)
+    if isinstance(lpb, int):
+        lpb = [lpb] * len(mults)
+    attn_res = cfg.get("attn_resolutions") or []
+    image_size = cfg["image_size"]
+    chans = [mc * m for m in mults]
+    enc, dec = [], []
+    cout = cfg["in_channels"] + 1
+    for level, (ch, nb) in enumerate(zip(chans, lpb)):
+        res = image_size // 2 ** level
+        if level == 0:
+            enc.append(dict(name=f"{res}x{res}_conv", kind="conv", cin=cout, cout=ch))
+            cout = ch
+        else:
+            enc.append(dict(name=f"{res}x{res}_down", kind="block", mode="enc", resample="down", cin=cout, cout=cout,
+                            attention=False))
+        for idx in range(nb):
+            enc.append(dict(name=f"{res}x{res}_block{idx}", kind="block", mode="enc", resample="keep", cin=cout,
+                            cout=ch, attention=(res in attn_res)))
+            cout = ch
+    skips = [b["cout"] for b in enc]
+    if not cfg.get("encode_only", False):
+        for level, (ch, nb) in reversed(list(enumerate(zip(chans, lpb)))):
+            res = image_size // 2 ** level
+            if level == len(chans) - 1:
+                dec.append(dict(name=f"{res}x{res}_in0", kind="block", mode="dec", resample="keep", cin=cout,
+                                cout=cout, attention=bool(cfg.get("midblock_attention", True)), concat=False))
+                dec.append(dict(name=f"{res}x{res}_in1", kind="block", mode="dec", resample="keep", cin=cout,
+                                cout=cout, attention=False, concat=False))
+            else:
+                dec.append(dict(name=f"{res}x{res}_up", kind="block", mode="dec", resample="up", cin=cout, cout=cout,
+                                attention=False, concat=False))
+            for idx in range(nb + 1):
+                sk = skips.pop()
+                dec.append(dict(name=f"{res}x{res}_block{idx}", kind="block", mode="dec", resample="keep",
+                                cin=cout + sk, cout=ch, attention=(res in attn_res), concat=True, skip_channels=sk))
+                cout = ch
+    return enc, dec
+
+
+class FoldedWeights:
+    """Device-resident effective weights of one model (fp32 small tensors + packed bf16 GEMM operands)."""
+
+    def __init__(self, model, device):
+        cfg = dict(model.config)
+        sd = {k: v.detach().to(device=device, dtype=torch.float32) for k, v in model.state_dict().items()}
+        self.cfg = cfg
+        self.device = device
+        enc, dec = block_plan(cfg)
+        bk = cfg.get("block_kwargs") or {}
+        for bad in ("conv_type", "resample_type", "activation", "no_padding", "expansion_factor"):
+            if bk.get(bad) not in (None, "default", "pooling", "silu", False, 1):
+                raise NotImplementedError(f"block_kwargs[{bad!r}]={bk[bad]!r} is not used by any shipped model and is "
+                                          "not implemented by the B200 path")
+        self.t_res = float(bk.get("res_balance", 0.3))
+        self.clip = float(bk.get("clip_act", 256.0) or 0.0)
+        self.cb = float(cfg.get("concat_balance", 0.3))
+        self.enc, self.dec = enc, dec
+        for b in enc + dec:
+            if b.get("attention") and b["cout"] // bk.get("channels_per_head", 64):
+                raise NotImplementedError(f"self-attention block {b['name']} (base/latent model) is not implemented yet "
+                                          "on the B200 path (SURVEY.md section 8f, rank 1)")
+        self.mc = cfg.get("model_channels", 128)
+        mults = cfg.get("model_channel_mults") or [1, 2, 3, 4]
+        self.emb_channels = cfg.get("emb_channels") or self.mc * max(mults)
+        self.noise_dims = self.mc if cfg.get("noise_emb_dims") is None else cfg["noise_emb_dims"]
+        self.has_cond = bool(cfg.get("conditional_inputs"))
+        self.pos_emb = cfg.get("fourier_scale", 1) == "pos"
+        self.in_channels = cfg["in_channels"]
+        self.out_channels = cfg.get("out_channels") or cfg["in_channels"]
+
+        t = self.t_res
+        nrm = math.sqrt((1 - t) ** 2 + t ** 2)
+        self.w_res = t / nrm
+        self.w_skip = (1 - t) / nrm
+
+        # map each encoder output to the decoder block that consumes it as a skip
+        idx = list(range(len(enc)))
+        self.skip_consumer = {}
+        for d in dec:
+            if d.get("concat"):
+                self.skip_consumer[idx.pop()] = d
+
+        g: dict = {}
+        self.g = g
+        if self.noise_dims > 0:
+            g["noise_linear"] = effective_weight(sd["noise_linear.weight"]).contiguous()
+            if self.pos_emb:
+                g["noise_freqs"] = sd["noise_fourier.freqs"].contiguous()
+        first = enc[0]
+        g["conv_in"] = effective_weight(sd[f"enc.{first['name']}.weight"]).contiguous()
+        out_gain = sd["out_gain"] if "out_gain" in sd else 1.0
+        g["conv_out"] = effective_weight(sd["out_conv.weight"], gain=out_gain).contiguous()
+        for side, blocks in (("enc", enc), ("dec", dec)):
+            for b in blocks:
+                if b["kind"] != "block":
+                    continue
+                p = f"{side}.{b['name']}."
+                if (p + "emb_linear.weight") in sd:
+                    g[p + "emb"] = effective_weight(sd[p + "emb_linear.weight"], gain=sd[p + "emb_gain"]).contiguous()
+                w0 = effective_weight(sd[p + "conv_res0.weight"])
+                w1 = effective_weight(sd[p + "conv_res1.weight"]) * self.w_res
+                ws = effective_weight(sd[p + "conv_skip.weight"]) if (p + "conv_skip.weight") in sd else None
+                if b["mode"] == "enc":
+                    if ws is not None:
+                        g[p + "k1"] = pack_weight_segments([ws])
+                    g[p + "res0"] = pack_weight_segments([w0])
+                    g[p + "res1"] = pack_weight_segments([w1])
+                else:
+                    if b.get("concat"):
+                        cs = b["skip_channels"]
+                        cx = b["cin"] - cs
+                        s1, s2 = mp_concat_scales(cx, cs, self.cb)
+                        g[p + "res0"] = pack_weight_segments([w0[:, :cx].contiguous(), w0[:, cx:].contiguous()])
+                        assert ws is not None
+                        g[p + "res1"] = pack_weight_segments([
+                            w1, (ws[:, :cx] * (s1 * self.w_skip)).contiguous(),
+                            (ws[:, cx:] * (s2 * self.w_skip)).contiguous()])
+                    else:
+                        assert ws is None, "decoder block without concat but with a skip conv is not planned"
+                        g[p + "res0"] = pack_weight_segments([w0])
+                        g[p + "res1"] = pack_weight_segments([w1])
+
+
+class UNetProgram:
+    """One compiled launch list (single forward, or a whole N-step solve) + the buffers it owns."""
+
+    def __init__(self):
+        self.handle = C.c_void_p()
+        L.check(L.lib().tdx_program_create(C.byref(self.handle)))
+        self.keep: list = []
+        self.n_igemm = 0
+        self.n_launch = 0
+
+    def run(self, use_graph: bool = True):
+        L.check(L.lib().tdx_program_run(self.handle, 1 if use_graph else 0, L.current_stream_ptr()))
+
+    def __del__(self):
+        try:
+            if self.handle:
+                L.lib().tdx_program_destroy(self.handle)
+                self.handle = C.c_void_p()
+        except Exception:
+            pass
+
+
+class UNetEmitter:
+    """Allocates the activation arena for (n, h, w) and appends the launches of one U-Net evaluation to a program."""
+
+    def __init__(self, fw: FoldedWeights, n: int, h: int, w: int):
+        levels = len(fw.cfg.get("model_channel_mults") or [1, 2, 3, 4])
+        need = 8 * 2 ** (levels - 1)
+        if h % need or w % need:
+            raise ValueError(f"spatial size {h}x{w} must be a multiple of {need} for this model")
+        self.fw, self.n, self.h, self.w = fw, n, h, w
+        self.dev = fw.device
+        self.arena: dict = {}
+        self.cvecs: dict = {}
+
+    def act(self, key, c, h, w):
+        if key not in self.arena:
+            self.arena[key] = torch.empty((self.n, c // 8, h, w, 8), dtype=torch.bfloat16, device=self.dev)
+        return self.arena[key]
+
+    def cvec(self, key, c):
+        if key not in self.cvecs:
+            self.cvecs[key] = torch.ones((self.n, c), dtype=torch.float32, device=self.dev)
+        return self.cvecs[key]
+
+    # ------------------------------------------------------------------ helpers
+    @staticmethod
+    def _set_out(desc, i, tensor, kind, spatial=L.SP_SAME, scale=1.0):
+        desc.out[i].ptr = tensor.data_ptr()
+        desc.out[i].kind = kind
+        desc.out[i].spatial = spatial
+        desc.out[i].scale = scale
+
+    def _next_spec(self, nxt, cur_c):
+        """(kind, spatial, scale) of the activated tensor the next stage reads, or None if it only reads RAW."""
+        if nxt is None:
+            return None
+        if nxt["mode"] == "enc":
+            if nxt["cin"] != nxt["cout"]:
+                return None
+            return (L.OUT_PNORM_SILU, L.SP_DOWN2 if nxt["resample"] == "down" else L.SP_SAME, 1.0)
+        if nxt.get("concat"):
+            s1, _ = mp_concat_scales(cur_c, nxt["skip_channels"], self.fw.cb)
+            return (L.OUT_SILU, L.SP_SAME, s1)
+        return (L.OUT_SILU, L.SP_UP2 if nxt["resample"] == "up" else L.SP_SAME, 1.0)
+
+    def _emit_outputs(self, desc, stage_key, c, h, w, nxt, enc_index):
+        """Fill desc.out[] for a block output; returns dict(raw=, act=, skip_act=)."""
+        res = {}
+        res["raw"] = self.act(stage_key + ".raw", c, h, w)
+        self._set_out(desc, 0, res["raw"], L.OUT_RAW)
+        slot = 1
+        spec = self._next_spec(nxt, c)
+        if spec is not None:
+            kind, spatial, scale = spec
+            hh, ww = (h // 2, w // 2) if spatial == L.SP_DOWN2 else ((h * 2, w * 2) if spatial == L.SP_UP2 else (h, w))
+            res["act"] = self.act(stage_key + ".act", c, hh, ww)
+            self._set_out(desc, slot, res["act"], kind, spatial, scale)
+            slot += 1
+        if enc_index is not None and enc_index in self.fw.skip_consumer:
+            d = self.fw.skip_consumer[enc_index]
+            cx = d["cin"] - d["skip_channels"]
+            _, s2 = mp_concat_scales(cx, d["skip_channels"], self.fw.cb)
+            res["skip_act"] = self.act(stage_key + ".skip_act", c, h, w)
+            self._set_out(desc, slot, res["skip_act"], L.OUT_SILU, L.SP_SAME, s2)
+            slot += 1
+        return res
+
+    def _igemm(self, prog, segs, packed, cout, h, w):
+        d = L.TdxIgemmDesc()
+        for i, (tensor, ch, taps) in enumerate(segs):
+            d.a_ptr[i] = tensor.data_ptr()
+            d.a_channels[i] = ch
+            d.a_taps[i] = taps
+        d.n_seg = len(segs)
+        d.b_packed = packed.data_ptr()
+        d.c_out = cout
+        d.n_img, d.height, d.width = self.n, h, w
+        return d
+
+    def _add_igemm(self, prog, d):
+        L.check(L.lib().tdx_program_add_igemm(prog.handle, C.byref(d)))
+        prog.n_igemm += 1
+        prog.n_launch += 1
+
+    # ------------------------------------------------------------------ one U-Net evaluation
+    def emit(self, prog: UNetProgram, srcs, labels=None, emb_in=None, model_out=None, sched=None):
+        """srcs: [(tensor NCHW fp32/bf16, channels, scale_ptr_tensor or None)] (1 or 2 sources);
+        labels: fp32 [n] device tensor (noise-only models); emb_in: fp32 [n, E] device tensor (conditional models);
+        model_out: fp32 [n, Cout, h, w] or None; sched: None or dict(coef=tensor[4], sample=tensor, x0_prev=tensor)."""
+        fw = self.fw
+        g = fw.g
+        n, dev = self.n, self.dev
+        seq = [("enc", i, b) for i, b in enumerate(fw.enc)] + [("dec", i, b) for i, b in enumerate(fw.dec)]
+
+        # ---- embedding / modulation vectors
+        blocks = [(side, b) for side, _, b in seq if b["kind"] == "block" and f"{side}.{b['name']}.emb" in g]
+        if blocks:
+            ed = L.TdxEmbedDesc()
+            arr = (L.TdxEmbedBlock * len(blocks))()
+            for i, (side, b) in enumerate(blocks):
+                key = f"{side}.{b['name']}."
+                arr[i].weight = g[key + "emb"].data_ptr()
+                arr[i].cvec = self.cvec(key, b["cout"]).data_ptr()
+                arr[i].c_out = b["cout"]
+            if emb_in is not None:
+                ed.emb_in = emb_in.data_ptr()
+            else:
+                if not (fw.pos_emb and fw.noise_dims > 0):
+                    raise ValueError("this model needs a host-computed embedding (emb_in)")
+                ed.noise_labels = labels.data_ptr()
+                ed.noise_weight = g["noise_linear"].data_ptr()
+                ed.noise_freqs = g["noise_freqs"].data_ptr()
+                ed.noise_dims = fw.noise_dims
+            ed.emb_channels = fw.emb_channels
+            ed.n_img = n
+            ed.n_blocks = len(blocks)
+            ed.blocks = arr
+            L.check(L.lib().tdx_program_add_embed(prog.handle, C.byref(ed)))
+            prog.n_launch += 1
+
+        h, w = self.h, self.w
+        cur = None
+        skips = []
+        for si, (side, idx, b) in enumerate(seq):
+            nxt = seq[si + 1][2] if si + 1 < len(seq) else None
+            key = f"{side}.{b['name']}."
+            enc_index = idx if side == "enc" else None
+            cout = b["cout"]
+            if b["kind"] == "conv":
+                cd = L.TdxConvInDesc()
+                tot = 0
+                for i, (tensor, ch, scale) in enumerate(srcs):
+                    cd.src[i] = tensor.data_ptr()
+                    cd.src_channels[i] = ch
+                    cd.src_dtype[i] = 0 if tensor.dtype == torch.float32 else 1
+                    cd.src_scale[i] = scale.data_ptr() if scale is not None else None
+                    tot += ch
+                assert tot + 1 == b["cin"], (tot, b["cin"])
+                cd.weight = g["conv_in"].data_ptr()
+                cd.c_out = cout
+                cd.n_img, cd.height, cd.width = n, h, w
+                cur = self._emit_outputs(cd, key, cout, h, w, nxt, enc_index)
+                L.check(L.lib().tdx_program_add_conv_in(prog.handle, C.byref(cd)))
+                prog.n_launch += 1
+            elif b["mode"] == "enc":
+                resid_sp = L.SP_SAME
+                if b["resample"] == "down":
+                    h, w = h // 2, w // 2
+                    resid_sp = L.SP_DOWN2
+                if (key + "k1") in g:
+                    d = self._igemm(prog, [(cur["raw"], b["cin"], 1)], g[key + "k1"], cout, h, w)
+                    d.epi_flags = L.EPI_PNORM
+                    xn = self.act(key + "xn", cout, h, w)
+                    a_in = self.act(key + "a0", cout, h, w)
+                    self._set_out(d, 0, xn, L.OUT_RAW)
+                    self._set_out(d, 1, a_in, L.OUT_SILU, L.SP_SAME, 1.0)
+                    self._add_igemm(prog, d)
+                    resid, resid_pn = xn, 0
+                else:
+                    a_in, resid, resid_pn = cur["act"], cur["raw"], 1
+                hbuf = self.act(key + "h", cout, h, w)
+                d = self._igemm(prog, [(a_in, cout, 9)], g[key + "res0"], cout, h, w)
+                d.epi_flags = L.EPI_EMB_SILU
+                d.cvec = self.cvec(key, cout).data_ptr()
+                self._set_out(d, 0, hbuf, L.OUT_RAW)
+                self._add_igemm(prog, d)
+                d = self._igemm(prog, [(hbuf, cout, 9)], g[key + "res1"], cout, h, w)
+                d.epi_flags = L.EPI_RESID
+                d.resid = resid.data_ptr()
+                d.resid_spatial = resid_sp
+                d.resid_pnorm = resid_pn
+                d.resid_scale = fw.w_skip
+                d.clip = fw.clip
+                cur = self._emit_outputs(d, key, cout, h, w, nxt, enc_index)
+                self._add_igemm(prog, d)
+            else:
+                resid_sp = L.SP_SAME
+                if b["resample"] == "up":
+                    h, w = h * 2, w * 2
+                    resid_sp = L.SP_UP2
+                hbuf = self.act(key + "h", cout, h, w)
+                if b.get("concat"):
+                    sk = skips.pop()
+                    cs = b["skip_channels"]
+                    cx = b["cin"] - cs
+                    segs0 = [(cur["act"], cx, 9), (sk["skip_act"], cs, 9)]
+                else:
+                    segs0 = [(cur["act"], b["cin"], 9)]
+                d = self._igemm(prog, segs0, g[key + "res0"], cout, h, w)
+                d.epi_flags = L.EPI_EMB_SILU
+                d.cvec = self.cvec(key, cout).data_ptr()
+                self._set_out(d, 0, hbuf, L.OUT_RAW)
+                self._add_igemm(prog, d)
+                if b.get("concat"):
+                    d = self._igemm(prog, [(hbuf, cout, 9), (cur["raw"], cx, 1), (sk["raw"], cs, 1)], g[key + "res1"],
+                                    cout, h, w)
+                else:
+                    d = self._igemm(prog, [(hbuf, cout, 9)], g[key + "res1"], cout, h, w)
+                    d.epi_flags = L.EPI_RESID
+                    d.resid = cur["raw"].data_ptr()
+                    d.resid_spatial = resid_sp
+                    d.resid_scale = fw.w_skip
+                d.clip = fw.clip
+                cur = self._emit_outputs(d, key, cout, h, w, nxt, None)
+                self._add_igemm(prog, d)
+            if side == "enc":
+                skips.append(cur)
+
+        od = L.TdxConvOutDesc()
+        od.x = cur["raw"].data_ptr()
+        od.c_in = seq[-1][2]["cout"]
+        od.weight = g["conv_out"].data_ptr()
+        od.c_out = fw.out_channels
+        od.n_img, od.height, od.width = n, h, w
+        if model_out is not None:
+            od.model_out = model_out.data_ptr()
+        if sched is not None:
+            od.sched_coef = sched["coef"].data_ptr()
+            od.sample = sched["sample"].data_ptr()
+            od.x0_prev = sched["x0_prev"].data_ptr()
+        L.check(L.lib().tdx_program_add_conv_out(prog.handle, C.byref(od)))
+        prog.n_launch += 1
+        prog.keep.append((self.arena, self.cvecs, fw, srcs, labels, emb_in, model_out, sched))

@@ -35,7 +35,7 @@ class Case:
     resid_spatial: int = L.SP_SAME
     resid_pnorm: int = 0
     resid_scale: float = 0.7
-    clip: float = 256.0
+    clip: float = 0.0
     outs: list = field(default_factory=lambda: [(L.OUT_RAW, L.SP_SAME, 1.0)])
     wscale: float = 1.0
     seed: int = 0
@@ -78,7 +78,9 @@ def reference(case: Case, acts, wts, cvec, resid):
             r = r[:, :, ::2, ::2]
         if case.resid_pnorm:
             r = pixelnorm(r)
-        v = torch.clamp(v + case.resid_scale * r, -case.clip, case.clip)
+        v = v + case.resid_scale * r
+    if case.clip > 0:
+        v = torch.clamp(v, -case.clip, case.clip)
     if case.epi & L.EPI_PNORM:
         v = pixelnorm(v)
     outs = []
@@ -163,4 +165,5 @@ def default_cases() -> list[Case]:
         Case("pnorm_1x1", [(64, 1)], 128, 1, 32, 32, epi=P,
              outs=[(L.OUT_RAW, L.SP_SAME, 1.0), (L.OUT_SILU, L.SP_SAME, 1.0)]),
         Case("clip_active", [(64, 9)], 64, 1, 16, 16, epi=R, clip=0.5),
+        Case("clip_no_resid", [(64, 9), (64, 1)], 64, 1, 16, 16, clip=0.3),
     ]

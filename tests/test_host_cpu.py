@@ -1,0 +1,124 @@
+"""CPU-side checks (run with -m "not gpu"): host logic of the product package, the C ABI surface, loud failure."""
+import ctypes as C
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import tiling as otile
+from oracle import unet as ounet
+from terrain_diffusion_b200 import _lib as L
+from terrain_diffusion_b200.inference import tiling as ptile
+from terrain_diffusion_b200.layout import from_nc8hw8, pack_weight_segments, to_nc8hw8
+from terrain_diffusion_b200.models import EDMUnet2D
+from terrain_diffusion_b200.models.plan import block_plan, effective_weight, mp_concat_scales
+from terrain_diffusion_b200.scheduler import EDMDPMSolverMultistepScheduler
+
+ROOT = Path(__file__).resolve().parent.parent
+G = np.load(ROOT / "tests" / "golden" / "reference_golden.npz")
+
+
+def test_library_exports_every_symbol_declared_in_header():
+    hdr = (ROOT / "include" / "tdx.h").read_text()
+    names = sorted(set(re.findall(r"\b(tdx_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(names) >= 20
+    lib = L.lib()
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+
+
+def test_abi_struct_sizes_match_ctypes():
+    lib = L.lib()
+    for i, st in enumerate(L.ABI_STRUCTS):
+        assert lib.tdx_abi_sizeof(i) == C.sizeof(st), st.__name__
+
+
+def test_descriptor_validation_runs_without_gpu():
+    d = L.TdxIgemmDesc()
+    assert L.lib().tdx_igemm_run(C.byref(d), None) == -1
+    d.n_seg = 1
+    d.a_ptr[0] = 16
+    d.a_channels[0] = 48
+    d.a_taps[0] = 9
+    assert L.lib().tdx_igemm_run(C.byref(d), None) == -1
+    assert b"multiple of 64" in L.lib().tdx_last_error()
+
+
+def test_model_refuses_cpu_tensors_loudly():
+    m = EDMUnet2D(**ounet.DECODER_CFG).eval()
+    with pytest.raises(L.TdxError):
+        m(torch.zeros(1, 5, 64, 64), torch.zeros(1), [])
+
+
+def test_model_state_dict_layout_matches_reference():
+    m = EDMUnet2D(**ounet.DECODER_CFG)
+    shapes = ounet.state_shapes(ounet.DECODER_CFG)
+    sd = m.state_dict()
+    assert set(sd) == set(shapes)
+    assert all(tuple(sd[k].shape) == tuple(shapes[k]) for k in sd)
+    assert m.count_parameters() == 27922533
+    assert m.config.model_channels == 64 and m.config.concat_balance == 0.5
+
+
+def test_block_plan_and_folding_match_oracle():
+    assert block_plan(ounet.DECODER_CFG) == ounet.block_plan(ounet.DECODER_CFG)
+    w = torch.randn(64, 128, 3, 3)
+    assert torch.equal(effective_weight(w, 0.7), ounet.effective_weight(w, 0.7))
+    assert mp_concat_scales(256, 192, 0.5) == ounet.mp_concat_scales(256, 192, 0.5)
+    # the closed-form scalars equal what mp_concat multiplies with
+    a, b = torch.ones(1, 256, 1, 1), torch.ones(1, 192, 1, 1)
+    cat = ounet.mp_concat([a, b], 0.5)
+    s1, s2 = mp_concat_scales(256, 192, 0.5)
+    assert abs(float(cat[0, 0, 0, 0]) - s1) < 1e-6 and abs(float(cat[0, -1, 0, 0]) - s2) < 1e-6
+
+
+def test_layout_roundtrip_and_weight_packing_order():
+    x = torch.randn(2, 64, 5, 7)
+    assert torch.equal(from_nc8hw8(to_nc8hw8(x)), x.bfloat16().float())
+    w = torch.arange(32 * 64 * 9, dtype=torch.float32).reshape(32, 64, 3, 3) / 1024
+    p = pack_weight_segments([w]).float().reshape(1, 9, 8, 32, 8)  # [chunk, tap, kgroup, n, e]
+    for (tap, kg, n, e) in [(0, 0, 0, 0), (4, 3, 17, 5), (8, 7, 31, 7)]:
+        assert p[0, tap, kg, n, e] == w[n, kg * 8 + e, tap // 3, tap % 3].bfloat16().float()
+
+
+def test_tiling_host_logic_is_bit_exact_with_reference_golden():
+    cases, lens, flat = G["tile_starts.cases"], G["tile_starts.lens"], G["tile_starts.flat"]
+    off = 0
+    for (length, tile, stride), n in zip(cases.tolist(), lens.tolist()):
+        assert ptile.tile_starts(length, tile, stride) == flat[off:off + n].tolist()
+        off += n
+    for size in (4, 8, 64):
+        np.testing.assert_array_equal(ptile.linear_weight_window(size).numpy(), G[f"window{size}"])
+    assert [ptile.padded_batch_size(n, 16) for n in (1, 2, 3, 5, 9, 16, 17)] == [1, 2, 4, 8, 16, 16, 16]
+    rows = [list(ptile.shard_rows(23, 8, r)) for r in range(8)]
+    assert sum(rows, []) == list(range(23))
+
+
+def test_window_range_integer_rule_matches_oracle_everywhere():
+    import random
+    rnd = random.Random(0)
+    for _ in range(3000):
+        a = rnd.randint(-600, 600)
+        b = a + rnd.randint(1, 700)
+        size, stride, off = rnd.randint(1, 90), rnd.randint(1, 90), rnd.randint(-9, 9)
+        assert list(ptile.window_range(a, b, size, stride, off)) == list(otile.window_range(a, b, size, stride, off))
+
+
+def test_scheduler_tables_and_errors_on_cpu():
+    for n in (4, 12, 20):
+        s = EDMDPMSolverMultistepScheduler()
+        s.set_timesteps(n)
+        np.testing.assert_array_equal(s.sigmas.numpy(), G[f"sched{n}.sigmas"])
+        np.testing.assert_array_equal(s.timesteps.numpy(), G[f"sched{n}.timesteps"])
+        np.testing.assert_array_equal(s.trigflow_precondition_noise(s.sigmas[:-1]).numpy(), G[f"sched{n}.cnoise"])
+        assert s.order_schedule() == [False] + [True] * (n - 2) + [False]
+    s = EDMDPMSolverMultistepScheduler()
+    with pytest.raises(ValueError):
+        s.step(torch.zeros(1), torch.tensor(0.0), torch.zeros(1))
+    s.set_timesteps(4)
+    with pytest.raises(L.TdxError):
+        s.step(torch.zeros(1), s.timesteps[0], torch.zeros(1))
+    with pytest.raises(NotImplementedError):
+        EDMDPMSolverMultistepScheduler(solver_order=3)
