@@ -183,6 +183,11 @@ int tdx_program_add_embed(TdxProgram* p, const TdxEmbedDesc* d);
 int tdx_program_num_launches(const TdxProgram* p);
 /* use_graph != 0: capture on first run, replay afterwards. */
 int tdx_program_run(TdxProgram* p, int use_graph, void* stream);
+/* Capture + instantiate + upload the graph without running it (keeps one-time costs out of timed regions). */
+int tdx_program_instantiate(TdxProgram* p, void* stream);
+/* Eager run with a CUDA event pair around every launch: ms_per_launch[i] = device time of launch i (in program
+ * order, tdx_program_num_launches entries); kinds[i] = 0 conv_in, 1 igemm, 2 conv_out, 3 embed.  Synchronises. */
+int tdx_program_profile(TdxProgram* p, float* ms_per_launch, int32_t* kinds, void* stream);
 int tdx_program_destroy(TdxProgram* p);
 
 #ifdef __cplusplus

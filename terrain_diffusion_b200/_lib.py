@@ -124,6 +124,10 @@ def _declare(l: C.CDLL) -> None:
     l.tdx_program_num_launches.argtypes = [C.c_void_p]
     l.tdx_program_run.restype = C.c_int
     l.tdx_program_run.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    l.tdx_program_instantiate.restype = C.c_int
+    l.tdx_program_instantiate.argtypes = [C.c_void_p, C.c_void_p]
+    l.tdx_program_profile.restype = C.c_int
+    l.tdx_program_profile.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int32), C.c_void_p]
     l.tdx_program_destroy.restype = C.c_int
     l.tdx_program_destroy.argtypes = [C.c_void_p]
 

@@ -124,38 +124,83 @@ extern "C" int tdx_program_add_embed(TdxProgram* p, const TdxEmbedDesc* d) {
 
 extern "C" int tdx_program_num_launches(const TdxProgram* p) { return p ? (int)p->ops.size() : -1; }
 
+static int ensure_graph(TdxProgram* p) {
+  if (p->exec) return TDX_OK;
+  // Capture on a private stream: the caller's stream may be the legacy default stream, which cannot be captured.
+  cudaStream_t cap = nullptr;
+  TDX_CHECK_CUDA(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
+  cudaError_t e = cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal);
+  if (e != cudaSuccess) {
+    cudaStreamDestroy(cap);
+    set_error("program: cudaStreamBeginCapture failed: %s", cudaGetErrorString(e));
+    return TDX_E_CUDA;
+  }
+  int rc = launch_all(p, cap);
+  cudaGraph_t g = nullptr;
+  e = cudaStreamEndCapture(cap, &g);
+  cudaStreamDestroy(cap);
+  if (rc != TDX_OK) {
+    if (g) cudaGraphDestroy(g);
+    return rc;
+  }
+  if (e != cudaSuccess) {
+    set_error("program: stream capture failed: %s", cudaGetErrorString(e));
+    return TDX_E_CUDA;
+  }
+  p->graph = g;
+  TDX_CHECK_CUDA(cudaGraphInstantiate(&p->exec, g, 0));
+  return TDX_OK;
+}
+
+extern "C" int tdx_program_instantiate(TdxProgram* p, void* stream_) {
+  TDX_REQUIRE(p, "program_instantiate: null program");
+  int rc = ensure_graph(p);
+  if (rc != TDX_OK) return rc;
+  TDX_CHECK_CUDA(cudaGraphUpload(p->exec, reinterpret_cast<cudaStream_t>(stream_)));
+  return TDX_OK;
+}
+
 extern "C" int tdx_program_run(TdxProgram* p, int use_graph, void* stream_) {
   TDX_REQUIRE(p, "program_run: null program");
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
   TDX_CHECK_CUDA(cudaStreamIsCapturing(stream, &st));
   if (!use_graph || st != cudaStreamCaptureStatusNone) return launch_all(p, stream);
-  if (!p->exec) {
-    // Capture on a private stream: the caller's stream may be the legacy default stream, which cannot be captured.
-    cudaStream_t cap = nullptr;
-    TDX_CHECK_CUDA(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
-    cudaError_t e = cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal);
-    if (e != cudaSuccess) {
-      cudaStreamDestroy(cap);
-      set_error("program_run: cudaStreamBeginCapture failed: %s", cudaGetErrorString(e));
-      return TDX_E_CUDA;
-    }
-    int rc = launch_all(p, cap);
-    cudaGraph_t g = nullptr;
-    e = cudaStreamEndCapture(cap, &g);
-    cudaStreamDestroy(cap);
-    if (rc != TDX_OK) {
-      if (g) cudaGraphDestroy(g);
-      return rc;
-    }
-    if (e != cudaSuccess) {
-      set_error("program_run: stream capture failed: %s", cudaGetErrorString(e));
-      return TDX_E_CUDA;
-    }
-    p->graph = g;
-    TDX_CHECK_CUDA(cudaGraphInstantiate(&p->exec, g, 0));
-  }
+  int rc = ensure_graph(p);
+  if (rc != TDX_OK) return rc;
   TDX_CHECK_CUDA(cudaGraphLaunch(p->exec, stream));
+  return TDX_OK;
+}
+
+extern "C" int tdx_program_profile(TdxProgram* p, float* ms_per_launch, int32_t* kinds, void* stream_) {
+  TDX_REQUIRE(p && ms_per_launch, "program_profile: null argument");
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  const size_t n = p->ops.size();
+  std::vector<cudaEvent_t> ev(n + 1);
+  for (auto& e : ev) TDX_CHECK_CUDA(cudaEventCreate(&e));
+  int rc = TDX_OK;
+  TDX_CHECK_CUDA(cudaEventRecord(ev[0], stream));
+  for (size_t i = 0; i < n && rc == TDX_OK; ++i) {
+    auto& op = p->ops[i];
+    switch (op.type) {
+      case OP_CONV_IN: rc = conv_in_launch(op.ci, stream); break;
+      case OP_IGEMM: rc = igemm_launch(op.ig, op.tms, stream); break;
+      case OP_CONV_OUT: rc = conv_out_launch(op.co, stream); break;
+      case OP_EMBED:
+        op.em.blocks = op.blocks.data();
+        rc = embed_launch(op.em, stream);
+        break;
+    }
+    cudaEventRecord(ev[i + 1], stream);
+    if (kinds) kinds[i] = (int32_t)op.type;
+  }
+  cudaError_t e = cudaStreamSynchronize(stream);
+  if (rc == TDX_OK && e == cudaSuccess) {
+    for (size_t i = 0; i < n; ++i) cudaEventElapsedTime(&ms_per_launch[i], ev[i], ev[i + 1]);
+  }
+  for (auto& evt : ev) cudaEventDestroy(evt);
+  if (rc != TDX_OK) return rc;
+  TDX_CHECK_CUDA(e);
   return TDX_OK;
 }
 

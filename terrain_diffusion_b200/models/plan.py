@@ -186,6 +186,17 @@ class UNetProgram:
     def run(self, use_graph: bool = True):
         L.check(L.lib().tdx_program_run(self.handle, 1 if use_graph else 0, L.current_stream_ptr()))
 
+    def instantiate(self):
+        L.check(L.lib().tdx_program_instantiate(self.handle, L.current_stream_ptr()))
+
+    def profile(self):
+        """Eager run with per-launch CUDA events: returns (ms list, kind list) in program order."""
+        n = L.lib().tdx_program_num_launches(self.handle)
+        ms = (C.c_float * n)()
+        kinds = (C.c_int32 * n)()
+        L.check(L.lib().tdx_program_profile(self.handle, ms, kinds, L.current_stream_ptr()))
+        return list(ms), list(kinds)
+
     def __del__(self):
         try:
             if self.handle:
