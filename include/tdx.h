@@ -38,7 +38,7 @@ int tdx_abi_sizeof(int which);
  * surrounding UNetBlock elementwise math, models/unet_block.py:116-156, fused into its epilogue).
  *
  * out[m, n] = sum over segments s, taps (r,c), channels k of  A_s[pixel(m)+(r-1,c-1), k] * B[n, s, k, r, c]
- *   m: output pixel inside a 16x8 tile (M = 128), n: output channel (N = Cout, whole), K = sum_s taps_s * C_s.
+ *   m: output pixel inside a 16x8 tile (M = 128), n: output channel (64 per work item), K = sum_s taps_s * C_s.
  * Up to 3 K-segments (e.g. the two halves of an mp_concat, or a 3x3 residual conv + a 1x1 skip conv fused as extra K).
  * ------------------------------------------------------------------------------------------------------------------ */
 enum { TDX_OUT_NONE = 0, TDX_OUT_RAW = 1, TDX_OUT_SILU = 2, TDX_OUT_PNORM_SILU = 3 };
@@ -59,9 +59,9 @@ typedef struct TdxIgemmDesc {
   int32_t a_channels[3];   /* multiple of 64 */
   int32_t a_taps[3];       /* 9 (3x3, pad 1) or 1 (1x1) */
   int32_t n_seg;
-  /* B operand: packed bf16 weights, stage order (segment, 64-channel chunk, tap), each stage [8][Cout][8] */
+  /* B operand: packed bf16 weights [Cout/64 slices][stage = (segment, 64-channel chunk, tap)][8][64][8] */
   const void* b_packed;
-  int32_t c_out;           /* multiple of 32, <= 256 */
+  int32_t c_out;           /* multiple of 64, <= 256 */
   int32_t n_img, height, width;   /* output == input spatial size; multiples of 8 */
   /* epilogue */
   int32_t epi_flags;       /* TDX_EPI_* */

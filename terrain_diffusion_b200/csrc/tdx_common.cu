@@ -2,6 +2,7 @@
 #include "tdx_common.h"
 
 #include <cudaTypedefs.h>
+#include <stdlib.h>
 #include <string.h>
 
 namespace tdx {
@@ -24,6 +25,30 @@ int sm_count() {
     if (n <= 0) n = 148;
   }
   return n;
+}
+
+static bool use_pdl() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("TDX_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
+void fill_launch_config(cudaLaunchConfig_t* cfg, cudaLaunchAttribute* attr, dim3 grid, dim3 block, size_t smem,
+                        cudaStream_t stream) {
+  memset(cfg, 0, sizeof(*cfg));
+  cfg->gridDim = grid;
+  cfg->blockDim = block;
+  cfg->dynamicSmemBytes = smem;
+  cfg->stream = stream;
+  if (use_pdl()) {
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg->attrs = attr;
+    cfg->numAttrs = 1;
+  }
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,

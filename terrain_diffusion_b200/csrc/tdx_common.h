@@ -30,6 +30,12 @@ int sm_count();
     }                                     \
   } while (0)
 
+// Launch configuration with programmatic dependent launch (PDL) enabled unless TDX_PDL=0: every libtdx kernel calls
+// griddepcontrol.wait before touching data produced by earlier kernels, so consecutive launches may overlap their
+// prologue (barrier init, TMEM allocation, weight prefetch) with the previous kernel's tail.
+void fill_launch_config(cudaLaunchConfig_t* cfg, cudaLaunchAttribute* attr, dim3 grid, dim3 block, size_t smem,
+                        cudaStream_t stream);
+
 // bf16 NC8HW8 activation -> 4-D tiled tensor map (dims: W*8 elems, H, C/8, N; box: 80 x 18 x 8 x 1).
 int make_act_tensor_map(CUtensorMap* out, const void* base, int n_img, int channels, int height, int width);
 

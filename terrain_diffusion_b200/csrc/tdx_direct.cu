@@ -33,6 +33,8 @@ __global__ void __launch_bounds__(128) conv_in_kernel(const ConvInParams p) {
     const int oc = i % CO, ci = (i / CO) % CI, tap = i / (CO * CI);
     ws[i] = p.weight[(oc * CI + ci) * 9 + tap];
   }
+  pdl_launch_dependents();
+  pdl_wait();  // the sources / scale come from earlier kernels; weights above are constants
   __syncthreads();
   const int img = blockIdx.y;
   const int pix = blockIdx.x * blockDim.x + threadIdx.x;
@@ -161,8 +163,10 @@ int conv_in_launch(const TdxConvInDesc& d, cudaStream_t stream) {
   int rc_prep = direct_prepare();
   if (rc_prep != TDX_OK) return rc_prep;
   dim3 grid((d.height * d.width + 127) / 128, d.n_img);
-  conv_in_kernel<<<grid, 128, smem, stream>>>(p);
-  TDX_CHECK_CUDA(cudaGetLastError());
+  cudaLaunchConfig_t cfg;
+  cudaLaunchAttribute attr[1];
+  fill_launch_config(&cfg, attr, grid, dim3(128), smem, stream);
+  TDX_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_in_kernel, p));
   return TDX_OK;
 }
 
@@ -192,6 +196,8 @@ __global__ void __launch_bounds__(128) conv_out_kernel(const ConvOutParams p) {
     const int oc = i & 7, c = (i >> 3) % C, tap = i / (8 * C);
     ws[i] = oc < p.cout ? p.weight[(oc * C + c) * 9 + tap] : 0.f;
   }
+  pdl_launch_dependents();
+  pdl_wait();
   __syncthreads();
   const int img = blockIdx.y;
   const int pix = blockIdx.x * blockDim.x + threadIdx.x;
@@ -274,8 +280,10 @@ int conv_out_launch(const TdxConvOutDesc& d, cudaStream_t stream) {
   int rc_prep = direct_prepare();
   if (rc_prep != TDX_OK) return rc_prep;
   dim3 grid((d.height * d.width + 127) / 128, d.n_img);
-  conv_out_kernel<<<grid, 128, smem, stream>>>(p);
-  TDX_CHECK_CUDA(cudaGetLastError());
+  cudaLaunchConfig_t cfg;
+  cudaLaunchAttribute attr[1];
+  fill_launch_config(&cfg, attr, grid, dim3(128), smem, stream);
+  TDX_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_out_kernel, p));
   return TDX_OK;
 }
 
@@ -297,6 +305,8 @@ __global__ void __launch_bounds__(256) embed_kernel(const __grid_constant__ Embe
   __shared__ float red[8];
   const int b = blockIdx.x, img = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_launch_dependents();
+  pdl_wait();  // labels / cvec buffers are shared with earlier launches
   if (p.emb_in) {
     for (int j = threadIdx.x; j < p.E; j += blockDim.x) emb[j] = p.emb_in[(size_t)img * p.E + j];
   } else {
@@ -368,8 +378,10 @@ int embed_launch(const TdxEmbedDesc& d, cudaStream_t stream) {
   p.E = d.emb_channels;
   for (int b = 0; b < d.n_blocks; ++b) p.blocks[b] = d.blocks[b];
   dim3 grid(d.n_blocks, d.n_img);
-  embed_kernel<<<grid, 256, 0, stream>>>(p);
-  TDX_CHECK_CUDA(cudaGetLastError());
+  cudaLaunchConfig_t cfg;
+  cudaLaunchAttribute attr[1];
+  fill_launch_config(&cfg, attr, grid, dim3(256), 0, stream);
+  TDX_CHECK_CUDA(cudaLaunchKernelEx(&cfg, embed_kernel, p));
   return TDX_OK;
 }
 

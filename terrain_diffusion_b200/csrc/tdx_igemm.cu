@@ -1,21 +1,31 @@
 // Persistent, warp-specialised implicit-GEMM convolution for sm_100a.
 //
-//   D[128 pixels x Cout] (fp32, TMEM) += A[128 x 16] (bf16, smem halo patch) * B[Cout x 16] (bf16, smem weights)
+//   D[128 pixels x 64 channels] (fp32, TMEM) += A[128 x 16] (bf16, smem halo patch) * B[64 x 16] (bf16, smem weights)
 //
-// * M tile = 16 rows x 8 columns of output pixels.  The A operand of every filter tap is the SAME (18 x 10)-pixel halo
-//   patch in shared memory: activations are stored NC8HW8, so TMA drops the patch as [kc][18][10][8ch] and the
-//   tcgen05 K-major/no-swizzle descriptor (8-row core matrices 128 B contiguous, SBO = 10 px * 16 B between pixel
-//   rows, LBO = one 8-channel plane) addresses tap (r,c) by just adding (r*10+c)*16 B to the start address.  The patch
-//   is fetched once per 64-channel chunk and used by all 9 taps (1.4x halo overhead instead of 9x re-fetch), and conv
-//   zero padding is TMA out-of-bounds fill.
-// * B (weights) are pre-packed on the host in exactly the shared-memory image order, one stage per (chunk, tap), and
-//   streamed with 1-D bulk copies through their own ring.
-// * Warp roles: w0 A-producer (TMA tiled), w1 B-producer (bulk copy), w2 MMA issuer (one thread), w3 TMEM allocator,
-//   w4..w7 epilogue (one TMEM lane quadrant each).  Two TMEM accumulators (2 x 256 columns) let the epilogue of tile i
-//   overlap the MMAs of tile i+1.
-// * Epilogue: each thread owns one pixel and ALL Cout channels, so the per-pixel channel reductions of the EDM2 block
-//   (pixel-norm) are thread-local; it applies emb-scale+mp_silu / residual mp_sum + clip / pixel-norm and writes up to
-//   three bf16 NC8HW8 outputs (raw, activated, activated+resampled) for the consumers.
+// * Work item = (M tile of 16 rows x 8 columns of output pixels) x (64-channel slice of Cout).  The slices of one
+//   M tile are adjacent work items, so they run concurrently on neighbouring CTAs and share the A patch in L2; small
+//   layers (32x32, 64x64 resolution) get Cout/64 times more CTAs this way.
+// * The A operand of every filter tap is the SAME (18 x 10)-pixel halo patch in shared memory: activations are stored
+//   NC8HW8, so TMA drops the patch as [kc][18][10][8ch] and the tcgen05 K-major/no-swizzle descriptor (8-row core
+//   matrices 128 B contiguous, SBO = 10 px * 16 B between pixel rows, LBO = one 8-channel plane) addresses tap (r,c)
+//   by just adding (r*10+c)*16 B to the start address.  The patch is fetched once per 64-channel chunk and used by all
+//   9 taps (1.4x halo overhead instead of 9x re-fetch); conv zero padding is TMA out-of-bounds fill.
+// * B (weights) are pre-packed on the host in exactly the shared-memory image order, one 8 KB stage per (chunk, tap),
+//   and streamed with 1-D bulk copies through their own ring.
+// * A K=16 tcgen05.mma has ~105 cycles of issue-to-issue latency when it accumulates into the tile the previous MMA
+//   wrote (measured: N=64 MMAs ran at 106 cycles instead of their 32-cycle throughput floor).  The four K=16 steps
+//   of a stage therefore accumulate into FOUR independent TMEM accumulators (4 x 64 columns) that the epilogue sums,
+//   so consecutive MMAs never depend on each other.  2 x (4 x 64) columns = all 512 TMEM columns, double-buffered so
+//   the epilogue of item i overlaps the MMAs of item i+1.
+// * Warp roles (all warp-converged, single-issuer instructions predicated on one elected lane): w0 A-producer (TMA
+//   tiled), w1 B-producer (bulk copy), w2 MMA issuer, w3 TMEM allocator, w4..w11 epilogue (two warps per TMEM lane
+//   quadrant, one 32-column chunk each).
+// * Epilogue: each thread owns one pixel; it applies emb-scale+mp_silu / residual mp_sum + clip / pixel-norm and
+//   writes up to three bf16 NC8HW8 outputs (raw, activated, activated+resampled) for the consumers.  Pixel-norm needs
+//   the sum of squares over ALL Cout channels: the Cout/64 CTAs of one M tile are then launched as a thread-block
+//   cluster and exchange their per-pixel partial sums through distributed shared memory + a cluster-scope mbarrier.
+// * Programmatic dependent launch: barrier init, TMEM allocation, descriptor prefetch and the weight stream of kernel
+//   N+1 overlap the tail of kernel N; griddepcontrol.wait guards everything that depends on earlier kernels.
 //
 // Reference math being replaced: models/mp_layers.py:201-221 (MPConv), models/unet_block.py:116-156 (UNetBlock).
 #include "tdx_common.h"
@@ -28,27 +38,42 @@ constexpr int kPatchH = kTileH + 2, kPatchW = kTileW + 2;
 constexpr int kKcBytes = kPatchH * kPatchW * 16;  // one 8-channel plane of the halo patch: 2880 B
 constexpr int kAStageBytes = 8 * kKcBytes;        // 64 channels: 23040 B
 constexpr int kSA = 3;                            // A ring depth
-constexpr int kMaxSB = 8;                         // B ring depth (max)
-constexpr int kThreads = 256;
-constexpr int kSmemBudget = 227 * 1024;
+constexpr int kSB = 12;                           // B ring depth
+constexpr int kNCta = 64;                         // output channels per work item (MMA N)
+constexpr int kBStageBytes = kNCta * 128;         // 64 rows x 64 K x bf16 = 8 KB
+constexpr int kAccCols = 4 * kNCta;               // 4 partial accumulators
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = 128 + 32 * kEpiWarps;
+constexpr int kMaxSplit = 4;
+constexpr int kSmemBytes = kSA * kAStageBytes + kSB * kBStageBytes + 8192;
 
 struct IgemmParams {
   int nseg;
   int seg_chunks[3];
   int seg_taps[3];
   const __nv_bfloat16* B;
-  int cout;
-  int H, W, nimg, tiles_x, tiles_y, num_tiles;
-  int SB;
+  int cout, nsplit;
+  int H, W, nimg, tiles_x, tiles_y, num_items;
+  int stages_per_item;
   int epi;
+  int cluster_stats;          // pixel-norm statistics are exchanged across the nsplit CTAs of a cluster
   const float* cvec;
   const uint4* resid;
   int resid_spatial, resid_pnorm;
   float resid_scale, clip;
   TdxOutSpec out[3];
+  int dbg;                    // debug experiment flags (tools/trace_igemm.py), normally 0
+  unsigned long long* trace;  // debug: per-item phase timestamps of CTA 0 (tools/trace_igemm.py), normally null
 };
 
-__device__ __forceinline__ void decode_tile(const IgemmParams& p, int tile, int& img, int& Y0, int& X0) {
+#define TDX_TRACE(slot, it)                                                                  \
+  do {                                                                                       \
+    if (p.trace && blockIdx.x == 0 && (it) < 16) p.trace[(it) * 8 + (slot)] = clock64();     \
+  } while (0)
+
+__device__ __forceinline__ void decode_item(const IgemmParams& p, int item, int& split, int& img, int& Y0, int& X0) {
+  split = item % p.nsplit;
+  int tile = item / p.nsplit;
   int tx = tile % p.tiles_x;
   int t = tile / p.tiles_x;
   int ty = t % p.tiles_y;
@@ -57,42 +82,123 @@ __device__ __forceinline__ void decode_tile(const IgemmParams& p, int tile, int&
   X0 = tx * kTileW;
 }
 
+// ---------------------------------------------------------------------------------------------- cluster helpers
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t local_smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_cluster_f32(uint32_t addr, float v) {
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t remote_bar_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote_bar_addr) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, P;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+// ---------------------------------------------------------------------------------------------- epilogue helpers
+struct OutCtx {
+  uint4* ptr;      // pixel address of this item's first channel group
+  size_t plane;    // uint4 stride between channel groups
+  int Wo;          // output row pitch (pixels)
+  int kind, spatial;
+  float hs, hsk;   // 0.5*scale, 0.5*scale/0.596 for the silu kinds
+  bool active;
+};
+
+__device__ __forceinline__ void store_group(const OutCtx& o, int group, const float* v, float hs, float hsk) {
+  float w[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) w[i] = (o.kind == TDX_OUT_RAW) ? v[i] : mp_silu_scaled(v[i], hs, hsk);
+  uint4 u;
+  u.x = pack_bf16x2(w[0], w[1]);
+  u.y = pack_bf16x2(w[2], w[3]);
+  u.z = pack_bf16x2(w[4], w[5]);
+  u.w = pack_bf16x2(w[6], w[7]);
+  uint4* dst = o.ptr + (size_t)group * o.plane;
+  dst[0] = u;
+  if (o.spatial == TDX_SP_UP2) {
+    dst[1] = u;
+    dst[o.Wo] = u;
+    dst[o.Wo + 1] = u;
+  }
+}
+
+// Sum of the four partial accumulators for 32 columns of this warp's lane quadrant.
+__device__ __forceinline__ void load_acc32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r0[32], r1[32];
+  tmem_ld32(taddr, r0);
+  tmem_ld32(taddr + kNCta, r1);
+  tmem_ld_wait();
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r0[i]) + __uint_as_float(r1[i]);
+  tmem_ld32(taddr + 2 * kNCta, r0);
+  tmem_ld32(taddr + 3 * kNCta, r1);
+  tmem_ld_wait();
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] += __uint_as_float(r0[i]) + __uint_as_float(r1[i]);
+}
+
 __global__ void __launch_bounds__(kThreads, 1)
 igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1,
              const __grid_constant__ CUtensorMap tm2, const __grid_constant__ IgemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* a_ring = smem;
   uint8_t* b_ring = smem + kSA * kAStageBytes;
-  const int b_stage_bytes = p.cout * 128;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(b_ring + p.SB * b_stage_bytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(b_ring + kSB * kBStageBytes);
   uint64_t* a_full = bars;
   uint64_t* a_empty = a_full + kSA;
   uint64_t* b_full = a_empty + kSA;
-  uint64_t* b_empty = b_full + kMaxSB;
-  uint64_t* t_full = b_empty + kMaxSB;
+  uint64_t* b_empty = b_full + kSB;
+  uint64_t* t_full = b_empty + kSB;
   uint64_t* t_empty = t_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+  uint64_t* x_full = t_empty + 2;                                     // [2] cluster statistics barriers
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(x_full + 2);
+  float* ssq = reinterpret_cast<float*>(bars) + 256;                  // [2 column halves][128 pixels]
+  float* stot = ssq + 256;                                            // [128] per-pixel totals for the second half
+  float* xstat = stot + 128;                                          // [2 parity][kMaxSplit][128] from peer CTAs
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = threadIdx.x >> 5;   // warp-uniform role id
   const int lane = threadIdx.x & 31;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&tm0);
     if (p.nseg > 1) tma_prefetch_desc(&tm1);
     if (p.nseg > 2) tma_prefetch_desc(&tm2);
   }
-  if (warp == 2 && lane == 0) {
+  if (warp == 2 && elect_one()) {
     for (int i = 0; i < kSA; ++i) {
       mbar_init(&a_full[i], 1);
       mbar_init(&a_empty[i], 1);
     }
-    for (int i = 0; i < p.SB; ++i) {
+    for (int i = 0; i < kSB; ++i) {
       mbar_init(&b_full[i], 1);
       mbar_init(&b_empty[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&t_full[i], 1);
-      mbar_init(&t_empty[i], 4);
+      mbar_init(&t_empty[i], kEpiWarps);
+      mbar_init(&x_full[i], p.nsplit > 1 ? (p.nsplit - 1) * 128 : 1);
     }
     fence_mbar_init();
   }
@@ -103,152 +209,235 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CU
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if (p.cluster_stats) cluster_sync_all();   // peers' barriers are initialised before anyone arrives on them
   const uint32_t tmem_base = *tmem_slot;
+  if (p.trace && blockIdx.x == 0 && threadIdx.x == 0) p.trace[127] = clock64();
+  // Let the next kernel in the stream start its own prologue as soon as SMs free up (it still waits for our memory).
+  pdl_launch_dependents();
 
   if (warp == 0) {
     // ------------------------------------------------------------------ A producer (halo patches via tiled TMA)
-    if (lane == 0) {
-      int sa = 0;
-      uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        int img, Y0, X0;
-        decode_tile(p, tile, img, Y0, X0);
-        for (int seg = 0; seg < p.nseg; ++seg) {
-          const CUtensorMap* tm = seg == 0 ? &tm0 : (seg == 1 ? &tm1 : &tm2);
-          for (int ch = 0; ch < p.seg_chunks[seg]; ++ch) {
-            mbar_wait(&a_empty[sa], ph ^ 1, 100 + sa);
+    pdl_wait();  // activations are produced by the previous kernel
+    int sa = 0;
+    uint32_t ph = 0;
+    int it = 0;
+    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
+      int split, img, Y0, X0;
+      decode_item(p, item, split, img, Y0, X0);
+      if (lane == 0) TDX_TRACE(0, it);
+      for (int seg = 0; seg < p.nseg; ++seg) {
+        const CUtensorMap* tm = seg == 0 ? &tm0 : (seg == 1 ? &tm1 : &tm2);
+        for (int ch = 0; ch < p.seg_chunks[seg]; ++ch) {
+          mbar_wait(&a_empty[sa], ph ^ 1, 100 + sa);
+          if (elect_one()) {
             mbar_expect_tx(&a_full[sa], kAStageBytes);
             tma_load_4d(tm, &a_full[sa], a_ring + sa * kAStageBytes, (X0 - 1) * 8, Y0 - 1, ch * 8, img);
-            if (++sa == kSA) { sa = 0; ph ^= 1; }
           }
+          __syncwarp();
+          if (++sa == kSA) { sa = 0; ph ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ B producer (pre-packed weight stages)
-    if (lane == 0) {
-      int sb = 0;
-      uint32_t ph = 0;
-      int stages_per_tile = 0;
-      for (int seg = 0; seg < p.nseg; ++seg) stages_per_tile += p.seg_chunks[seg] * p.seg_taps[seg];
-      const uint8_t* bsrc = reinterpret_cast<const uint8_t*>(p.B);
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        for (int ks = 0; ks < stages_per_tile; ++ks) {
-          mbar_wait(&b_empty[sb], ph ^ 1, 200 + sb);
-          mbar_expect_tx(&b_full[sb], b_stage_bytes);
-          bulk_load_1d(bsrc + (size_t)ks * b_stage_bytes, &b_full[sb], b_ring + sb * b_stage_bytes, b_stage_bytes);
-          if (++sb == p.SB) { sb = 0; ph ^= 1; }
+    // Weights are constants: no dependency on the previous kernel, so this starts streaming during its tail.
+    int sb = 0;
+    uint32_t ph = 0;
+    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+      const int split = item % p.nsplit;
+      const uint8_t* bsrc = reinterpret_cast<const uint8_t*>(p.B) + (size_t)split * p.stages_per_item * kBStageBytes;
+      for (int ks = 0; ks < p.stages_per_item; ++ks) {
+        mbar_wait(&b_empty[sb], ph ^ 1, 200 + sb);
+        if (elect_one()) {
+          if (p.dbg & 2) {
+            mbar_arrive(&b_full[sb]);
+          } else {
+            mbar_expect_tx(&b_full[sb], kBStageBytes);
+            bulk_load_1d(bsrc + (size_t)ks * kBStageBytes, &b_full[sb], b_ring + sb * kBStageBytes, kBStageBytes);
+          }
         }
+        __syncwarp();
+        if (++sb == kSB) { sb = 0; ph ^= 1; }
       }
     }
   } else if (warp == 2) {
-    // ------------------------------------------------------------------ MMA issuer (single thread)
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(128, p.cout);
-      const uint32_t b_lbo = p.cout * 16;
-      int sa = 0, sb = 0;
-      uint32_t pha = 0, phb = 0;
-      int it = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-        const int acc = it & 1;
-        const uint32_t accph = (it >> 1) & 1;
-        mbar_wait(&t_empty[acc], accph ^ 1, 300 + acc);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * 256;
-        uint32_t accumulate = 0;
-        for (int seg = 0; seg < p.nseg; ++seg) {
-          const int taps = p.seg_taps[seg];
-          for (int ch = 0; ch < p.seg_chunks[seg]; ++ch) {
-            mbar_wait(&a_full[sa], pha, 400 + sa);
+    // ------------------------------------------------------------------ MMA issuer (one elected lane issues)
+    const uint32_t idesc = make_idesc_bf16(128, kNCta);
+    constexpr uint32_t b_lbo = kNCta * 16;
+    const uint32_t a_sbo = (p.dbg & 1) ? 128 : kPatchW * 16;
+    int sa = 0, sb = 0;
+    uint32_t pha = 0, phb = 0;
+    int it = 0;
+    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t accph = (it >> 1) & 1;
+      mbar_wait(&t_empty[acc], accph ^ 1, 300 + acc);
+      tc_fence_after();
+      if (lane == 0) TDX_TRACE(1, it);
+      const uint32_t d_tmem = tmem_base + acc * kAccCols;
+      uint32_t accumulate = 0;
+      for (int seg = 0; seg < p.nseg; ++seg) {
+        const int taps = p.seg_taps[seg];
+        for (int ch = 0; ch < p.seg_chunks[seg]; ++ch) {
+          mbar_wait(&a_full[sa], pha, 400 + sa);
+          tc_fence_after();
+          if (lane == 0 && seg == 0 && ch == 0) TDX_TRACE(2, it);
+          const uint32_t a_base = smem_u32(a_ring + sa * kAStageBytes);
+          for (int tap = 0; tap < taps; ++tap) {
+            const int r = taps == 9 ? tap / 3 : 1;
+            const int c = taps == 9 ? tap % 3 : 1;
+            mbar_wait(&b_full[sb], phb, 500 + sb);
             tc_fence_after();
-            const uint32_t a_base = smem_u32(a_ring + sa * kAStageBytes);
-            for (int tap = 0; tap < taps; ++tap) {
-              const int r = taps == 9 ? tap / 3 : 1;
-              const int c = taps == 9 ? tap % 3 : 1;
-              mbar_wait(&b_full[sb], phb, 500 + sb);
-              tc_fence_after();
-              const uint32_t b_base = smem_u32(b_ring + sb * b_stage_bytes);
-              const uint32_t a_tap = a_base + (r * kPatchW + c) * 16;
+            const uint32_t b_base = smem_u32(b_ring + sb * kBStageBytes);
+            const uint32_t a_tap = a_base + (r * kPatchW + c) * 16;
+            if (elect_one()) {
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
-                const uint64_t adesc = make_smem_desc(a_tap + 2 * j * kKcBytes, kKcBytes, kPatchW * 16);
+                // K step j accumulates into partial accumulator j: no MMA depends on its predecessor
+                const uint64_t adesc = make_smem_desc(a_tap + 2 * j * kKcBytes, kKcBytes, a_sbo);
                 const uint64_t bdesc = make_smem_desc(b_base + 2 * j * b_lbo, b_lbo, 128);
-                umma_bf16(d_tmem, adesc, bdesc, idesc, accumulate);
-                accumulate = 1;
+                umma_bf16(d_tmem + j * kNCta, adesc, bdesc, idesc, accumulate);
               }
               umma_commit(&b_empty[sb]);
-              if (++sb == p.SB) { sb = 0; phb ^= 1; }
             }
-            umma_commit(&a_empty[sa]);
-            if (++sa == kSA) { sa = 0; pha ^= 1; }
+            __syncwarp();
+            accumulate = 1;
+            if (++sb == kSB) { sb = 0; phb ^= 1; }
           }
+          if (elect_one()) umma_commit(&a_empty[sa]);
+          __syncwarp();
+          if (++sa == kSA) { sa = 0; pha ^= 1; }
         }
-        umma_commit(&t_full[acc]);
       }
+      if (elect_one()) umma_commit(&t_full[acc]);
+      __syncwarp();
+      if (lane == 0) TDX_TRACE(3, it);
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue (TMEM -> registers -> global)
+    // warp w and w+4 share TMEM lane quadrant (w & 3); `half` selects which 32 of the item's 64 columns a warp owns.
+    pdl_wait();  // residual / cvec come from earlier kernels; our stores must not race their readers
     const int q = warp & 3;
+    const int half = (warp - 4) >> 2;
     const int m = q * 32 + lane;
     const int y = m >> 3, x = m & 7;
     const int C8 = p.cout >> 3;
     const bool need_norm = (p.epi & TDX_EPI_PNORM) || p.out[0].kind == TDX_OUT_PNORM_SILU ||
                            p.out[1].kind == TDX_OUT_PNORM_SILU || p.out[2].kind == TDX_OUT_PNORM_SILU;
-    const int npass = need_norm ? 2 : 1;
+    const bool fast_res0 = (p.epi == TDX_EPI_EMB_SILU) && p.clip <= 0.f && p.out[0].kind == TDX_OUT_RAW &&
+                           p.out[0].spatial == TDX_SP_SAME && p.out[1].kind == TDX_OUT_NONE &&
+                           p.out[2].kind == TDX_OUT_NONE;
+    const uint32_t my_rank = p.cluster_stats ? cluster_ctarank() : 0;
     int it = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
       const int acc = it & 1;
       const uint32_t accph = (it >> 1) & 1;
-      int img, Y0, X0;
-      decode_tile(p, tile, img, Y0, X0);
+      int split, img, Y0, X0;
+      decode_item(p, item, split, img, Y0, X0);
       const int Y = Y0 + y, X = X0 + x;
       const bool valid = (Y < p.H) && (X < p.W);
+      const int ch0 = split * kNCta + half * 32;          // first output channel this warp produces
+      const int g0 = ch0 >> 3;                            // its first channel group
+      const uint32_t taddr = tmem_base + acc * kAccCols + half * 32 + ((uint32_t)(q * 32) << 16);
+      const float* cv = p.cvec ? p.cvec + (size_t)img * p.cout + ch0 : nullptr;
 
-      // residual addressing (+ optional pixel-norm of the residual vector)
-      const uint4* rptr = nullptr;
-      size_t rplane = 0;
-      float rscale = p.resid_scale;
-      if ((p.epi & TDX_EPI_RESID) && valid) {
-        int Hr = p.H, Wr = p.W, Yr = Y, Xr = X;
-        if (p.resid_spatial == TDX_SP_UP2) { Hr = p.H >> 1; Wr = p.W >> 1; Yr = Y >> 1; Xr = X >> 1; }
-        else if (p.resid_spatial == TDX_SP_DOWN2) { Hr = p.H << 1; Wr = p.W << 1; Yr = Y << 1; Xr = X << 1; }
-        rplane = (size_t)Hr * Wr;
-        rptr = p.resid + ((size_t)img * C8) * rplane + (size_t)Yr * Wr + Xr;
-        if (p.resid_pnorm) {
-          float ss = 0.f;
-          for (int g = 0; g < C8; ++g) {
-            uint4 u = __ldg(rptr + g * rplane);
-            float a, b;
-            unpack_bf16x2(u.x, a, b); ss += a * a + b * b;
-            unpack_bf16x2(u.y, a, b); ss += a * a + b * b;
-            unpack_bf16x2(u.z, a, b); ss += a * a + b * b;
-            unpack_bf16x2(u.w, a, b); ss += a * a + b * b;
-          }
-          rscale = p.resid_scale / (1e-4f + sqrtf(ss / (float)p.cout));
-        }
-      }
-
-      mbar_wait(&t_full[acc], accph, 600 + acc);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + acc * 256 + ((uint32_t)(q * 32) << 16);
-      const float* cv = p.cvec ? p.cvec + (size_t)img * p.cout : nullptr;
-
-      float sumsq = 0.f, inv = 1.f;
-      for (int pass = 0; pass < npass; ++pass) {
-        const bool last = (pass == npass - 1);
-        if (need_norm && last) inv = 1.0f / (1e-4f + sqrtf(sumsq / (float)p.cout));
-        for (int c0 = 0; c0 < p.cout; c0 += 32) {
-          uint32_t r[32];
-          __syncwarp();
-          tmem_ld32(taddr + c0, r);
-          tmem_ld_wait();
-          float v[32];
+      if (fast_res0) {
+        // ---------------- res0: v = mp_silu(acc * c) -> one bf16 output (the common case: half of all launches)
+        const size_t oplane = (size_t)p.H * p.W;
+        uint4* optr = reinterpret_cast<uint4*>(p.out[0].ptr) + ((size_t)img * C8 + g0) * oplane + (size_t)Y * p.W + X;
+        float4 c4[8];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+        for (int i = 0; i < 8; ++i) c4[i] = __ldg(reinterpret_cast<const float4*>(cv) + i);
+        if (warp == 4 && lane == 0) TDX_TRACE(4, it);
+        mbar_wait(&t_full[acc], accph, 600 + acc);
+        tc_fence_after();
+        if (warp == 4 && lane == 0) TDX_TRACE(5, it);
+        if (!(p.dbg & 4)) {
+          float v[32];
+          __syncwarp();
+          load_acc32(taddr, v);
+          if (valid) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const float4 ca = c4[2 * g], cb = c4[2 * g + 1];
+              float w[8];
+              w[0] = mp_silu_f(v[g * 8 + 0] * ca.x);
+              w[1] = mp_silu_f(v[g * 8 + 1] * ca.y);
+              w[2] = mp_silu_f(v[g * 8 + 2] * ca.z);
+              w[3] = mp_silu_f(v[g * 8 + 3] * ca.w);
+              w[4] = mp_silu_f(v[g * 8 + 4] * cb.x);
+              w[5] = mp_silu_f(v[g * 8 + 5] * cb.y);
+              w[6] = mp_silu_f(v[g * 8 + 6] * cb.z);
+              w[7] = mp_silu_f(v[g * 8 + 7] * cb.w);
+              uint4 u;
+              u.x = pack_bf16x2(w[0], w[1]);
+              u.y = pack_bf16x2(w[2], w[3]);
+              u.z = pack_bf16x2(w[4], w[5]);
+              u.w = pack_bf16x2(w[6], w[7]);
+              optr[(size_t)g * oplane] = u;
+            }
+          }
+        }
+      } else {
+        // ---------------- general: residual mp_sum (+pixel-norm of the residual), clip, pixel-norm, up to 3 outputs
+        const uint4* rptr = nullptr;
+        size_t rplane = 0;
+        float rscale = p.resid_scale;
+        if ((p.epi & TDX_EPI_RESID) && valid) {
+          int Hr = p.H, Wr = p.W, Yr = Y, Xr = X;
+          if (p.resid_spatial == TDX_SP_UP2) { Hr = p.H >> 1; Wr = p.W >> 1; Yr = Y >> 1; Xr = X >> 1; }
+          else if (p.resid_spatial == TDX_SP_DOWN2) { Hr = p.H << 1; Wr = p.W << 1; Yr = Y << 1; Xr = X << 1; }
+          rplane = (size_t)Hr * Wr;
+          const uint4* rbase = p.resid + ((size_t)img * C8) * rplane + (size_t)Yr * Wr + Xr;
+          if (p.resid_pnorm) {
+            // the residual's pixel-norm runs over ALL Cout channels (every split reads them; L2-resident)
+            float ss = 0.f;
+            for (int g = 0; g < C8; ++g) {
+              uint4 u = __ldg(rbase + g * rplane);
+              float a, b;
+              unpack_bf16x2(u.x, a, b); ss = fmaf(a, a, fmaf(b, b, ss));
+              unpack_bf16x2(u.y, a, b); ss = fmaf(a, a, fmaf(b, b, ss));
+              unpack_bf16x2(u.z, a, b); ss = fmaf(a, a, fmaf(b, b, ss));
+              unpack_bf16x2(u.w, a, b); ss = fmaf(a, a, fmaf(b, b, ss));
+            }
+            rscale = p.resid_scale / (1e-4f + sqrtf(ss / (float)p.cout));
+          }
+          rptr = rbase + (size_t)g0 * rplane;
+        }
+        OutCtx oc[3];
+#pragma unroll
+        for (int o = 0; o < 3; ++o) {
+          const TdxOutSpec& os = p.out[o];
+          oc[o].kind = os.kind;
+          oc[o].spatial = os.spatial;
+          oc[o].active = (os.kind != TDX_OUT_NONE) && valid;
+          int Ho = p.H, Wo = p.W, Yo = Y, Xo = X;
+          if (os.spatial == TDX_SP_DOWN2) {
+            if ((Y | X) & 1) oc[o].active = false;
+            Ho >>= 1; Wo >>= 1; Yo >>= 1; Xo >>= 1;
+          } else if (os.spatial == TDX_SP_UP2) {
+            Ho <<= 1; Wo <<= 1; Yo <<= 1; Xo <<= 1;
+          }
+          oc[o].plane = (size_t)Ho * Wo;
+          oc[o].Wo = Wo;
+          oc[o].ptr = reinterpret_cast<uint4*>(os.ptr) + ((size_t)img * C8 + g0) * oc[o].plane + (size_t)Yo * Wo + Xo;
+          oc[o].hs = 0.5f * os.scale;
+          oc[o].hsk = 0.5f * os.scale * (1.0f / 0.596f);
+        }
+
+        if (warp == 4 && lane == 0) TDX_TRACE(4, it);
+        mbar_wait(&t_full[acc], accph, 600 + acc);
+        tc_fence_after();
+        if (warp == 4 && lane == 0) TDX_TRACE(5, it);
+
+        if (!(p.dbg & 4)) {
+          float v[32];
+          __syncwarp();
+          load_acc32(taddr, v);
           if (p.epi & TDX_EPI_EMB_SILU) {
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
-              float4 c4 = __ldg(reinterpret_cast<const float4*>(cv + c0 + i));
+              float4 c4 = __ldg(reinterpret_cast<const float4*>(cv + i));
               v[i + 0] = mp_silu_f(v[i + 0] * c4.x);
               v[i + 1] = mp_silu_f(v[i + 1] * c4.y);
               v[i + 2] = mp_silu_f(v[i + 2] * c4.z);
@@ -258,7 +447,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CU
           if (p.epi & TDX_EPI_RESID) {
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
-              uint4 u = valid ? __ldg(rptr + (size_t)((c0 >> 3) + g) * rplane) : make_uint4(0, 0, 0, 0);
+              uint4 u = valid ? __ldg(rptr + (size_t)g * rplane) : make_uint4(0, 0, 0, 0);
               float rr[8];
               unpack_bf16x2(u.x, rr[0], rr[1]);
               unpack_bf16x2(u.y, rr[2], rr[3]);
@@ -272,64 +461,71 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CU
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = fminf(fmaxf(v[i], -p.clip), p.clip);
           }
-          if (need_norm && !last) {
+          float inv = 1.f;
+          if (need_norm) {
+            float sumsq = 0.f;
 #pragma unroll
             for (int i = 0; i < 32; ++i) sumsq = fmaf(v[i], v[i], sumsq);
-            continue;
+            // (1) combine the two 32-column halves of this CTA (warps w and w+4 own the same pixels)
+            ssq[half * 128 + m] = sumsq;
+            named_bar_sync(1 + q, 64);
+            float tot = ssq[m] + ssq[128 + m];
+            if (p.cluster_stats) {
+              // (2) combine the Cout/64 CTAs of this M tile through distributed shared memory
+              const int par = it & 1;
+              if (half == 0) {
+                for (uint32_t r = 0; r < (uint32_t)p.nsplit; ++r) {
+                  if (r == my_rank) continue;
+                  st_cluster_f32(map_to_cta(smem_u32(&xstat[(par * kMaxSplit + my_rank) * 128 + m]), r), tot);
+                  mbar_arrive_cluster(map_to_cta(smem_u32(&x_full[par]), r));
+                }
+                const uint32_t xph = (it >> 1) & 1;
+                if (!mbar_try_wait_cluster(&x_full[par], xph)) {
+                  long long t0 = clock64();
+                  while (!mbar_try_wait_cluster(&x_full[par], xph)) {
+                    if (clock64() - t0 > TDX_WAIT_LIMIT) {
+                      printf("tdx: cluster statistics wait timeout block=%d\n", (int)blockIdx.x);
+                      __trap();
+                    }
+                  }
+                }
+                for (uint32_t r = 0; r < (uint32_t)p.nsplit; ++r)
+                  if (r != my_rank) tot += xstat[(par * kMaxSplit + r) * 128 + m];
+                stot[m] = tot;
+              }
+              named_bar_sync(5 + q, 64);
+              tot = stot[m];
+            }
+            inv = 1.0f / (1e-4f + sqrtf(tot / (float)p.cout));
           }
           if (p.epi & TDX_EPI_PNORM) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] *= inv;
           }
-          if (!valid) continue;
 #pragma unroll
           for (int o = 0; o < 3; ++o) {
-            const TdxOutSpec& os = p.out[o];
-            if (os.kind == TDX_OUT_NONE) continue;
-            float sc = os.scale;
-            if (os.kind == TDX_OUT_PNORM_SILU) sc = (p.epi & TDX_EPI_PNORM) ? 1.0f : inv;
-            int Ho = p.H, Wo = p.W, Yo = Y, Xo = X;
-            if (os.spatial == TDX_SP_DOWN2) {
-              if ((Y | X) & 1) continue;
-              Ho >>= 1; Wo >>= 1; Yo >>= 1; Xo >>= 1;
-            } else if (os.spatial == TDX_SP_UP2) {
-              Ho <<= 1; Wo <<= 1; Yo <<= 1; Xo <<= 1;
+            if (!oc[o].active) continue;
+            float hs = oc[o].hs, hsk = oc[o].hsk;
+            if (oc[o].kind == TDX_OUT_PNORM_SILU) {
+              const float sc = (p.epi & TDX_EPI_PNORM) ? 1.0f : inv;
+              hs = 0.5f * sc;
+              hsk = 0.5f * sc * (1.0f / 0.596f);
             }
-            const size_t oplane = (size_t)Ho * Wo;
-            uint4* optr = reinterpret_cast<uint4*>(os.ptr) + ((size_t)img * C8 + (c0 >> 3)) * oplane +
-                          (size_t)Yo * Wo + Xo;
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              float w[8];
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                float t = v[g * 8 + i];
-                w[i] = (os.kind == TDX_OUT_RAW) ? t : mp_silu_f(t * sc);
-              }
-              uint4 u;
-              u.x = pack_bf16x2(w[0], w[1]);
-              u.y = pack_bf16x2(w[2], w[3]);
-              u.z = pack_bf16x2(w[4], w[5]);
-              u.w = pack_bf16x2(w[6], w[7]);
-              uint4* dst = optr + (size_t)g * oplane;
-              dst[0] = u;
-              if (os.spatial == TDX_SP_UP2) {
-                dst[1] = u;
-                dst[Wo] = u;
-                dst[Wo + 1] = u;
-              }
-            }
+            for (int g = 0; g < 4; ++g) store_group(oc[o], g, v + g * 8, hs, hsk);
           }
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&t_empty[acc]);
+      if (warp == 4 && lane == 0) TDX_TRACE(6, it);
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  if (p.cluster_stats) cluster_sync_all();   // nobody leaves while a peer may still write into its shared memory
   if (warp == 3) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
@@ -337,47 +533,46 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CU
 }
 
 // ---------------------------------------------------------------------------------------------------- host side
-static int smem_layout(int cout, int* SB_out) {
-  const int fixed = kSA * kAStageBytes + 1024;  // rings + barriers/tmem slot
-  int SB = (kSmemBudget - fixed) / (cout * 128);
-  if (SB > kMaxSB) SB = kMaxSB;
-  if (SB < 2) return -1;
-  *SB_out = SB;
-  int bytes = kSA * kAStageBytes + SB * cout * 128 + 1024;
-  if (bytes < 120 * 1024) bytes = 120 * 1024;  // one CTA per SM: each CTA allocates all 512 TMEM columns
-  return bytes;
-}
+static unsigned long long* g_trace_ptr = nullptr;
+static int g_dbg_flags = 0;
 
 int igemm_prepare() {
   static bool attr_set = false;
   if (!attr_set) {
-    TDX_CHECK_CUDA(cudaFuncSetAttribute(igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+    TDX_CHECK_CUDA(cudaFuncSetAttribute(igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     attr_set = true;
   }
   return TDX_OK;
+}
+
+static bool needs_norm(const TdxIgemmDesc& d) {
+  if (d.epi_flags & TDX_EPI_PNORM) return true;
+  for (int o = 0; o < 3; ++o)
+    if (d.out[o].kind == TDX_OUT_PNORM_SILU) return true;
+  return false;
 }
 
 int igemm_launch(const TdxIgemmDesc& d, const CUtensorMap* tms, cudaStream_t stream) {
   IgemmParams p;
   memset(&p, 0, sizeof(p));
   p.nseg = d.n_seg;
+  p.stages_per_item = 0;
   for (int s = 0; s < d.n_seg; ++s) {
     p.seg_chunks[s] = d.a_channels[s] / 64;
     p.seg_taps[s] = d.a_taps[s];
+    p.stages_per_item += p.seg_chunks[s] * p.seg_taps[s];
   }
   p.B = reinterpret_cast<const __nv_bfloat16*>(d.b_packed);
   p.cout = d.c_out;
+  p.nsplit = d.c_out / kNCta;
   p.H = d.height;
   p.W = d.width;
   p.nimg = d.n_img;
   p.tiles_x = (d.width + kTileW - 1) / kTileW;
   p.tiles_y = (d.height + kTileH - 1) / kTileH;
-  p.num_tiles = p.tiles_x * p.tiles_y * d.n_img;
-  int SB = 0;
-  const int smem = smem_layout(d.c_out, &SB);
-  TDX_REQUIRE(smem > 0, "igemm: c_out=%d does not fit the shared-memory plan", d.c_out);
-  p.SB = SB;
+  p.num_items = p.tiles_x * p.tiles_y * d.n_img * p.nsplit;
   p.epi = d.epi_flags;
+  p.cluster_stats = (needs_norm(d) && p.nsplit > 1) ? 1 : 0;
   p.cvec = d.cvec;
   p.resid = reinterpret_cast<const uint4*>(d.resid);
   p.resid_spatial = d.resid_spatial;
@@ -385,15 +580,29 @@ int igemm_launch(const TdxIgemmDesc& d, const CUtensorMap* tms, cudaStream_t str
   p.resid_scale = d.resid_scale;
   p.clip = d.clip;
   for (int o = 0; o < 3; ++o) p.out[o] = d.out[o];
+  p.trace = g_trace_ptr;
+  p.dbg = g_dbg_flags;
 
   int rc_prep = igemm_prepare();
   if (rc_prep != TDX_OK) return rc_prep;
-  int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
+  // grid: one CTA per SM at most, a multiple of nsplit so the splits of an M tile always run side by side
+  int grid = p.num_items < sm_count() ? p.num_items : sm_count();
+  grid -= grid % p.nsplit;
   const CUtensorMap& t0 = tms[0];
   const CUtensorMap& t1 = tms[d.n_seg > 1 ? 1 : 0];
   const CUtensorMap& t2 = tms[d.n_seg > 2 ? 2 : 0];
-  igemm_kernel<<<grid, kThreads, smem, stream>>>(t0, t1, t2, p);
-  TDX_CHECK_CUDA(cudaGetLastError());
+  cudaLaunchConfig_t cfg;
+  cudaLaunchAttribute attr[2];
+  fill_launch_config(&cfg, attr, dim3(grid), dim3(kThreads), kSmemBytes, stream);
+  if (p.cluster_stats) {
+    attr[cfg.numAttrs].id = cudaLaunchAttributeClusterDimension;
+    attr[cfg.numAttrs].val.clusterDim.x = p.nsplit;
+    attr[cfg.numAttrs].val.clusterDim.y = 1;
+    attr[cfg.numAttrs].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs += 1;
+  }
+  TDX_CHECK_CUDA(cudaLaunchKernelEx(&cfg, igemm_kernel, t0, t1, t2, p));
   return TDX_OK;
 }
 
@@ -406,8 +615,8 @@ int igemm_validate(const TdxIgemmDesc& d) {
     TDX_REQUIRE(d.a_taps[s] == 9 || d.a_taps[s] == 1, "igemm: a_taps[%d]=%d not 9 or 1", s, d.a_taps[s]);
   }
   TDX_REQUIRE(d.b_packed != nullptr, "igemm: b_packed is null");
-  TDX_REQUIRE(d.c_out >= 32 && d.c_out <= 256 && d.c_out % 32 == 0, "igemm: c_out=%d must be a multiple of 32 <= 256",
-              d.c_out);
+  TDX_REQUIRE(d.c_out >= 64 && d.c_out <= 64 * kMaxSplit && d.c_out % 64 == 0,
+              "igemm: c_out=%d must be a multiple of 64 <= %d", d.c_out, 64 * kMaxSplit);
   TDX_REQUIRE(d.n_img >= 1 && d.height >= 8 && d.width >= 8 && d.height % 8 == 0 && d.width % 8 == 0,
               "igemm: bad shape n=%d h=%d w=%d (h, w multiples of 8)", d.n_img, d.height, d.width);
   if (d.epi_flags & TDX_EPI_EMB_SILU) TDX_REQUIRE(d.cvec != nullptr, "igemm: EMB_SILU needs cvec");
@@ -427,6 +636,12 @@ int igemm_validate(const TdxIgemmDesc& d) {
 }
 
 }  // namespace tdx
+
+// Debug hooks (tools/trace_igemm.py): device buffer of 128 u64 that CTA 0 fills with per-item phase clocks.
+extern "C" void tdx_debug_set_igemm_trace(void* device_u64x128) {
+  tdx::g_trace_ptr = reinterpret_cast<unsigned long long*>(device_u64x128);
+}
+extern "C" void tdx_debug_set_igemm_flags(int flags) { tdx::g_dbg_flags = flags; }
 
 extern "C" int64_t tdx_igemm_packed_weight_elems(const int32_t* a_channels, const int32_t* a_taps, int32_t n_seg,
                                                  int32_t c_out) {

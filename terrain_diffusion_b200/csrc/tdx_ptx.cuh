@@ -156,9 +156,30 @@ __device__ __forceinline__ uint32_t make_idesc_bf16(uint32_t m, uint32_t n) {
 }
 
 // ---------------------------------------------------------------- math
-// mp_silu(x) = silu(x) / 0.596                                        (reference: models/mp_layers.py:33-34)
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// mp_silu(s*x) = silu(s*x) / 0.596                                    (reference: models/mp_layers.py:33-34)
+// silu(z) = z*sigmoid(z) = h*tanh(h) + h with h = z/2: one MUFU op (tanh.approx, rel. error 2^-11 -- far inside the
+// bf16 rounding of the stored result) instead of ex2 + rcp.
+__device__ __forceinline__ float mp_silu_scaled(float x, float half_s, float half_s_k) {
+  const float h = x * half_s;
+  const float hk = x * half_s_k;
+  return fmaf(hk, tanh_approx(h), hk);
+}
 __device__ __forceinline__ float mp_silu_f(float x) {
-  return __fdividef(x * (1.0f / 0.596f), 1.0f + __expf(-x));
+  return mp_silu_scaled(x, 0.5f, 0.5f / 0.596f);
+}
+
+// Programmatic dependent launch (PDL): let the next kernel's prologue overlap this kernel's tail, and wait for the
+// previous kernel's memory before touching anything it produced.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {

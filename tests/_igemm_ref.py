@@ -164,6 +164,12 @@ def default_cases() -> list[Case]:
              outs=[(L.OUT_RAW, L.SP_SAME, 1.0), (L.OUT_SILU, L.SP_UP2, 1.2)]),
         Case("pnorm_1x1", [(64, 1)], 128, 1, 32, 32, epi=P,
              outs=[(L.OUT_RAW, L.SP_SAME, 1.0), (L.OUT_SILU, L.SP_SAME, 1.0)]),
+        Case("cluster4_pnorm_persistent", [(256, 9)], 256, 2, 64, 64, epi=R, resid_pnorm=1,
+             outs=[(L.OUT_RAW, L.SP_SAME, 1.0), (L.OUT_PNORM_SILU, L.SP_SAME, 1.0), (L.OUT_SILU, L.SP_SAME, 0.7)]),
+        Case("cluster3_pnorm_down2", [(192, 9)], 192, 1, 32, 32, epi=R, resid_spatial=L.SP_DOWN2, resid_pnorm=1,
+             outs=[(L.OUT_RAW, L.SP_SAME, 1.0), (L.OUT_PNORM_SILU, L.SP_DOWN2, 1.0)]),
+        Case("cluster4_k1_pnorm", [(192, 1)], 256, 1, 32, 32, epi=P,
+             outs=[(L.OUT_RAW, L.SP_SAME, 1.0), (L.OUT_SILU, L.SP_SAME, 1.0)]),
         Case("clip_active", [(64, 9)], 64, 1, 16, 16, epi=R, clip=0.5),
         Case("clip_no_resid", [(64, 9), (64, 1)], 64, 1, 16, 16, clip=0.3),
     ]

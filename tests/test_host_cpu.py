@@ -77,10 +77,14 @@ def test_block_plan_and_folding_match_oracle():
 def test_layout_roundtrip_and_weight_packing_order():
     x = torch.randn(2, 64, 5, 7)
     assert torch.equal(from_nc8hw8(to_nc8hw8(x)), x.bfloat16().float())
-    w = torch.arange(32 * 64 * 9, dtype=torch.float32).reshape(32, 64, 3, 3) / 1024
-    p = pack_weight_segments([w]).float().reshape(1, 9, 8, 32, 8)  # [chunk, tap, kgroup, n, e]
-    for (tap, kg, n, e) in [(0, 0, 0, 0), (4, 3, 17, 5), (8, 7, 31, 7)]:
-        assert p[0, tap, kg, n, e] == w[n, kg * 8 + e, tap // 3, tap % 3].bfloat16().float()
+    w = (torch.arange(128 * 128 * 9, dtype=torch.float32).reshape(128, 128, 3, 3) % 509) / 64
+    w1 = (torch.arange(128 * 64, dtype=torch.float32).reshape(128, 64, 1, 1) % 251) / 32
+    p = pack_weight_segments([w, w1]).float().reshape(2, -1)  # [split][stages...]
+    p3 = p[:, :2 * 9 * 8 * 64 * 8].reshape(2, 2, 9, 8, 64, 8)  # [split, chunk, tap, kgroup, n, e]
+    for (s_, ch, tap, kg, n, e) in [(0, 0, 0, 0, 0, 0), (1, 1, 4, 3, 17, 5), (0, 1, 8, 7, 63, 7), (1, 0, 2, 5, 40, 1)]:
+        assert p3[s_, ch, tap, kg, n, e] == w[s_ * 64 + n, ch * 64 + kg * 8 + e, tap // 3, tap % 3].bfloat16().float()
+    p1 = p[:, 2 * 9 * 8 * 64 * 8:].reshape(2, 1, 1, 8, 64, 8)
+    assert p1[1, 0, 0, 2, 9, 3] == w1[64 + 9, 2 * 8 + 3, 0, 0].bfloat16().float()
 
 
 def test_tiling_host_logic_is_bit_exact_with_reference_golden():

@@ -1,0 +1,58 @@
+"""Per-tile phase timeline of CTA 0 of the igemm kernel (debug hook tdx_debug_set_igemm_trace)."""
+import ctypes as C
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+from terrain_diffusion_b200 import _lib as L
+from terrain_diffusion_b200.layout import pack_weight_segments, to_nc8hw8
+
+SHAPES = [("64->64 @256", [(64, 9)], 64, 256), ("128->128 @128", [(128, 9)], 128, 128),
+          ("256->256 @32", [(256, 9)], 256, 32), ("192->192 @64", [(192, 9)], 192, 64)]
+NAMES = ["A-prod start", "mma: tmem free", "mma: A landed", "mma: issued+commit", "epi: waiting", "epi: acc ready",
+         "epi: done"]
+
+
+def main():
+    dev = torch.device("cuda:0")
+    lib = L.lib()
+    lib.tdx_debug_set_igemm_trace.argtypes = [C.c_void_p]
+    trace = torch.zeros(128, dtype=torch.int64, device=dev)
+    flags = int(sys.argv[1]) if len(sys.argv) > 1 else 0
+    lib.tdx_debug_set_igemm_flags(flags)
+    print('### debug flags', flags)
+    for name, segs, cout, res in SHAPES:
+        acts = [to_nc8hw8(torch.randn(1, c, res, res, device=dev)) for c, _ in segs]
+        wts = [torch.randn(cout, c, 3, 3, device=dev) * 0.02 for c, t in segs]
+        b = pack_weight_segments(wts)
+        out = torch.empty(1, cout // 8, res, res, 8, dtype=torch.bfloat16, device=dev)
+        cvec = torch.ones(1, cout, device=dev)
+        d = L.TdxIgemmDesc()
+        for i, (c, t) in enumerate(segs):
+            d.a_ptr[i] = acts[i].data_ptr(); d.a_channels[i] = c; d.a_taps[i] = t
+        d.n_seg = len(segs); d.b_packed = b.data_ptr(); d.c_out = cout
+        d.n_img, d.height, d.width = 1, res, res
+        d.epi_flags = L.EPI_EMB_SILU; d.cvec = cvec.data_ptr()
+        d.out[0].ptr = out.data_ptr(); d.out[0].kind = L.OUT_RAW; d.out[0].scale = 1.0
+        for _ in range(2):
+            L.check(lib.tdx_igemm_run(C.byref(d), L.current_stream_ptr()))
+        torch.cuda.synchronize()
+        trace.zero_()
+        lib.tdx_debug_set_igemm_trace(trace.data_ptr())
+        L.check(lib.tdx_igemm_run(C.byref(d), L.current_stream_ptr()))
+        torch.cuda.synchronize()
+        lib.tdx_debug_set_igemm_trace(None)
+        t = trace.cpu().tolist()
+        t0 = t[127]
+        print(f"== {name}: clocks relative to CTA-0 setup done")
+        for it in range(2):
+            row = t[it * 8: it * 8 + 7]
+            if row[0] == 0 and row[1] == 0:
+                break
+            print(f"  tile {it}: " + "  ".join(f"{n}={v - t0 if v else -1}" for n, v in zip(NAMES, row)))
+
+
+if __name__ == "__main__":
+    main()
