@@ -91,8 +91,8 @@ typedef struct TdxConvInDesc {
   int32_t src_channels[2];   /* channels of each source (second may be 0) */
   int32_t src_dtype[2];      /* 0 = fp32, 1 = bf16 */
   const float* src_scale[2]; /* optional DEVICE scalar multiplied into source i (precondition_inputs), or NULL */
-  const float* weight;       /* fp32 effective weights [c_out][sum(src_channels)+1][3][3] (ones channel last) */
-  int32_t c_out;             /* multiple of 32, <= 256 */
+  const float* weight;       /* fp32 effective weights, tap-major [3*3][sum(src_channels)+1][c_out] (ones channel last) */
+  int32_t c_out;             /* multiple of 64, <= 256; sum(src_channels) <= 15 */
   int32_t n_img, height, width;
   TdxOutSpec out[3];         /* same semantics as TdxIgemmDesc.out (TDX_SP_SAME only) */
 } TdxConvInDesc;
@@ -108,7 +108,7 @@ int tdx_conv_in_run(const TdxConvInDesc* desc, void* stream);
 typedef struct TdxConvOutDesc {
   const void* x;           /* bf16 NC8HW8, n_img x c_in x H x W */
   int32_t c_in;            /* multiple of 8 */
-  const float* weight;     /* fp32 effective weights [c_out][c_in][3][3] */
+  const float* weight;     /* fp32 effective weights, tap-major [3*3][c_in][c_out == 1 ? 1 : 8] (zero padded) */
   int32_t c_out;           /* 1..8 */
   int32_t n_img, height, width;
   float* model_out;        /* fp32 NCHW [n_img][c_out][H][W] or NULL */
@@ -125,7 +125,7 @@ int tdx_conv_out_run(const TdxConvOutDesc* desc, void* stream);
  *     c_b  = emb_linear_b(emb)*gain_b + 1 ;  c_b /= sqrt(mean(c_b^2) + 1e-8)          for every block b
  * ------------------------------------------------------------------------------------------------------------------ */
 typedef struct TdxEmbedBlock {
-  const float* weight;   /* fp32 effective [c_out][emb_channels], emb_gain folded */
+  const float* weight;   /* fp32 effective, TRANSPOSED [emb_channels][c_out], emb_gain folded */
   float* cvec;           /* fp32 [n_img][c_out] */
   int32_t c_out;
   int32_t _pad;
@@ -133,7 +133,7 @@ typedef struct TdxEmbedBlock {
 typedef struct TdxEmbedDesc {
   const float* noise_labels;   /* DEVICE fp32 [n_img] (trigflow t); used when emb_in is NULL */
   const float* emb_in;         /* DEVICE fp32 [n_img][emb_channels] precomputed embedding, or NULL */
-  const float* noise_weight;   /* fp32 effective [emb_channels][noise_dims] */
+  const float* noise_weight;   /* fp32 effective, TRANSPOSED [noise_dims][emb_channels] */
   const float* noise_freqs;    /* DEVICE fp32 [noise_dims/2]: the model's MPPositionalEmbedding.freqs buffer */
   int32_t noise_dims;          /* even, <= 256 */
   int32_t emb_channels;        /* <= 1024 */

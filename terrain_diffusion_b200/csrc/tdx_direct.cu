@@ -9,6 +9,8 @@ namespace tdx {
 __device__ __forceinline__ float mp_silu_precise(float x) { return x / (1.0f + expf(-x)) / 0.596f; }
 
 // ------------------------------------------------------------------------------------------------ first conv
+constexpr int kConvInGroups = 4;   // 32-pixel groups per block (amortises the weight staging)
+
 struct ConvInParams {
   const void* src[2];
   int src_ch[2];
@@ -26,26 +28,94 @@ __device__ __forceinline__ float load_in(const void* base, int dtype, size_t idx
   return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(base)[idx]);
 }
 
+// Block = 128 threads = 32 consecutive pixels x 4 warps; warp w computes output channels [oc0 + 16w, oc0 + 16w + 16)
+// of each 64-channel group, so weights are warp-broadcast shared-memory reads and every store is a 512-byte row of
+// 16-byte pixel vectors.
+template <int CI>
 __global__ void __launch_bounds__(128) conv_in_kernel(const ConvInParams p) {
   extern __shared__ float ws[];  // [tap][ci][cout]
-  const int CI = p.ci, CO = p.cout;
-  for (int i = threadIdx.x; i < 9 * CI * CO; i += blockDim.x) {
-    const int oc = i % CO, ci = (i / CO) % CI, tap = i / (CO * CI);
-    ws[i] = p.weight[(oc * CI + ci) * 9 + tap];
-  }
+  __shared__ float ssq[4][32];
+  const int CO = p.cout;
+  for (int i = threadIdx.x; i < (9 * CI * CO) / 4; i += blockDim.x)
+    reinterpret_cast<float4*>(ws)[i] = __ldg(reinterpret_cast<const float4*>(p.weight) + i);
   pdl_launch_dependents();
   pdl_wait();  // the sources / scale come from earlier kernels; weights above are constants
   __syncthreads();
   const int img = blockIdx.y;
-  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
-  if (pix >= p.H * p.W) return;
-  const int y = pix / p.W, x = pix % p.W;
+  const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
+  for (int grp = 0; grp < kConvInGroups; ++grp) {
+  const int pix = (blockIdx.x * kConvInGroups + grp) * 32 + lane;
+  const bool inb = pix < p.H * p.W;
+  const int y = inb ? pix / p.W : 0, x = inb ? pix % p.W : 0;
   const size_t plane = (size_t)p.H * p.W;
   const float s0 = p.src_scale[0] ? __ldg(p.src_scale[0]) : 1.0f;
   const float s1 = p.src_scale[1] ? __ldg(p.src_scale[1]) : 1.0f;
   const int c0n = p.src_ch[0], c1n = p.src_ch[1];
   const int C8 = CO >> 3;
+
   float sumsq = 0.f;
+  for (int oc0 = 0; oc0 < CO; oc0 += 64) {
+    const int oc = oc0 + wq * 16;
+    float acc[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+#pragma unroll 1
+    for (int tap = 0; tap < 9; ++tap) {
+      // the CI input values of this tap (zero padded at the border, ones channel included), loaded as one batch
+      const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
+      const bool ok = inb && yy >= 0 && yy < p.H && xx >= 0 && xx < p.W;
+      const size_t off = (size_t)yy * p.W + xx;
+      float in[CI];
+#pragma unroll
+      for (int ci = 0; ci < CI; ++ci) {
+        float v = 0.f;
+        if (ok) {
+          if (ci < c0n) v = load_in(p.src[0], p.src_dtype[0], ((size_t)img * c0n + ci) * plane + off) * s0;
+          else if (ci < c0n + c1n) v = load_in(p.src[1], p.src_dtype[1], ((size_t)img * c1n + (ci - c0n)) * plane + off) * s1;
+          else v = 1.0f;
+        }
+        in[ci] = v;
+      }
+#pragma unroll
+      for (int ci = 0; ci < CI; ++ci) {
+        {
+          const float v = in[ci];
+          const float4* w4 = reinterpret_cast<const float4*>(ws + (tap * CI + ci) * CO + oc);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 w = w4[j];
+            acc[4 * j + 0] = fmaf(w.x, v, acc[4 * j + 0]);
+            acc[4 * j + 1] = fmaf(w.y, v, acc[4 * j + 1]);
+            acc[4 * j + 2] = fmaf(w.z, v, acc[4 * j + 2]);
+            acc[4 * j + 3] = fmaf(w.w, v, acc[4 * j + 3]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) sumsq = fmaf(acc[j], acc[j], sumsq);
+    if (inb) {
+#pragma unroll
+      for (int o = 0; o < 3; ++o) {
+        const TdxOutSpec& os = p.out[o];
+        if (os.kind != TDX_OUT_RAW && os.kind != TDX_OUT_SILU) continue;
+        uint4* optr = reinterpret_cast<uint4*>(os.ptr) + ((size_t)img * C8 + (oc >> 3)) * plane + pix;
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          float w[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float t = acc[g * 8 + i];
+            w[i] = os.kind == TDX_OUT_RAW ? t : mp_silu_f(t * os.scale);
+          }
+          uint4 u;
+          u.x = pack_bf16x2(w[0], w[1]); u.y = pack_bf16x2(w[2], w[3]);
+          u.z = pack_bf16x2(w[4], w[5]); u.w = pack_bf16x2(w[6], w[7]);
+          optr[(size_t)g * plane] = u;
+        }
+      }
+    }
+  }
   bool want_pnorm = false;
   const uint4* raw_ptr = nullptr;
 #pragma unroll
@@ -53,73 +123,37 @@ __global__ void __launch_bounds__(128) conv_in_kernel(const ConvInParams p) {
     if (p.out[o].kind == TDX_OUT_PNORM_SILU) want_pnorm = true;
     if (p.out[o].kind == TDX_OUT_RAW) raw_ptr = reinterpret_cast<const uint4*>(p.out[o].ptr);
   }
-
-  for (int oc0 = 0; oc0 < CO; oc0 += 32) {
-    float acc[32];
+  if (want_pnorm) {
+    // per-pixel sum of squares over all channels = sum over the 4 warps; then re-read this warp's own raw outputs
+    ssq[wq][lane] = sumsq;
+    __syncthreads();
+    const float tot = ssq[0][lane] + ssq[1][lane] + ssq[2][lane] + ssq[3][lane];
+    const float inv = 1.0f / (1e-4f + sqrtf(tot / (float)CO));
+    if (inb) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) acc[j] = 0.f;
-    for (int tap = 0; tap < 9; ++tap) {
-      const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
-      if (yy < 0 || yy >= p.H || xx < 0 || xx >= p.W) continue;  // zero padding (also of the ones channel)
-      const size_t off = (size_t)yy * p.W + xx;
-      for (int ci = 0; ci < CI; ++ci) {
-        float v;
-        if (ci < c0n) v = load_in(p.src[0], p.src_dtype[0], ((size_t)img * c0n + ci) * plane + off) * s0;
-        else if (ci < c0n + c1n) v = load_in(p.src[1], p.src_dtype[1], ((size_t)img * c1n + (ci - c0n)) * plane + off) * s1;
-        else v = 1.0f;
-        const float4* w4 = reinterpret_cast<const float4*>(ws + (tap * CI + ci) * CO + oc0);
+      for (int o = 0; o < 3; ++o) {
+        const TdxOutSpec& os = p.out[o];
+        if (os.kind != TDX_OUT_PNORM_SILU) continue;
+        for (int oc0 = 0; oc0 < CO; oc0 += 64) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 w = w4[j];
-          acc[4 * j + 0] = fmaf(w.x, v, acc[4 * j + 0]);
-          acc[4 * j + 1] = fmaf(w.y, v, acc[4 * j + 1]);
-          acc[4 * j + 2] = fmaf(w.z, v, acc[4 * j + 2]);
-          acc[4 * j + 3] = fmaf(w.w, v, acc[4 * j + 3]);
+          for (int g = 0; g < 2; ++g) {
+            const size_t idx = ((size_t)img * C8 + ((oc0 + wq * 16) >> 3) + g) * plane + pix;
+            const uint4 u = raw_ptr[idx];
+            float a[8];
+            unpack_bf16x2(u.x, a[0], a[1]); unpack_bf16x2(u.y, a[2], a[3]);
+            unpack_bf16x2(u.z, a[4], a[5]); unpack_bf16x2(u.w, a[6], a[7]);
+            uint4 r;
+            r.x = pack_bf16x2(mp_silu_f(a[0] * inv), mp_silu_f(a[1] * inv));
+            r.y = pack_bf16x2(mp_silu_f(a[2] * inv), mp_silu_f(a[3] * inv));
+            r.z = pack_bf16x2(mp_silu_f(a[4] * inv), mp_silu_f(a[5] * inv));
+            r.w = pack_bf16x2(mp_silu_f(a[6] * inv), mp_silu_f(a[7] * inv));
+            reinterpret_cast<uint4*>(os.ptr)[idx] = r;
+          }
         }
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < 32; ++j) sumsq = fmaf(acc[j], acc[j], sumsq);
-#pragma unroll
-    for (int o = 0; o < 3; ++o) {
-      const TdxOutSpec& os = p.out[o];
-      if (os.kind != TDX_OUT_RAW && os.kind != TDX_OUT_SILU) continue;
-      uint4* optr = reinterpret_cast<uint4*>(os.ptr) + ((size_t)img * C8 + (oc0 >> 3)) * plane + pix;
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        float w[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float t = acc[g * 8 + i];
-          w[i] = os.kind == TDX_OUT_RAW ? t : mp_silu_f(t * os.scale);
-        }
-        uint4 u;
-        u.x = pack_bf16x2(w[0], w[1]); u.y = pack_bf16x2(w[2], w[3]);
-        u.z = pack_bf16x2(w[4], w[5]); u.w = pack_bf16x2(w[6], w[7]);
-        optr[(size_t)g * plane] = u;
       }
     }
   }
-  if (want_pnorm) {
-    // second pass over this thread's own raw output (bf16) -- the raw output is always requested alongside
-    const float inv = 1.0f / (1e-4f + sqrtf(sumsq / (float)CO));
-#pragma unroll
-    for (int o = 0; o < 3; ++o) {
-      const TdxOutSpec& os = p.out[o];
-      if (os.kind != TDX_OUT_PNORM_SILU) continue;
-      for (int g = 0; g < C8; ++g) {
-        const uint4 u = raw_ptr[((size_t)img * C8 + g) * plane + pix];
-        float a[8];
-        unpack_bf16x2(u.x, a[0], a[1]); unpack_bf16x2(u.y, a[2], a[3]);
-        unpack_bf16x2(u.z, a[4], a[5]); unpack_bf16x2(u.w, a[6], a[7]);
-        uint4 r;
-        r.x = pack_bf16x2(mp_silu_f(a[0] * inv), mp_silu_f(a[1] * inv));
-        r.y = pack_bf16x2(mp_silu_f(a[2] * inv), mp_silu_f(a[3] * inv));
-        r.z = pack_bf16x2(mp_silu_f(a[4] * inv), mp_silu_f(a[5] * inv));
-        r.w = pack_bf16x2(mp_silu_f(a[6] * inv), mp_silu_f(a[7] * inv));
-        reinterpret_cast<uint4*>(os.ptr)[((size_t)img * C8 + g) * plane + pix] = r;
-      }
-    }
+  __syncthreads();  // ssq is reused by the next pixel group
   }
 }
 
@@ -129,7 +163,10 @@ int conv_in_validate(const TdxConvInDesc& d) {
   TDX_REQUIRE(d.src[0] && d.src_channels[0] > 0, "conv_in: src[0] missing");
   TDX_REQUIRE(d.src_channels[1] == 0 || d.src[1], "conv_in: src[1] missing");
   TDX_REQUIRE(d.weight, "conv_in: weight is null");
-  TDX_REQUIRE(d.c_out >= 32 && d.c_out <= 256 && d.c_out % 32 == 0, "conv_in: c_out=%d", d.c_out);
+  TDX_REQUIRE(d.c_out >= 64 && d.c_out <= 256 && d.c_out % 64 == 0, "conv_in: c_out=%d (multiple of 64)", d.c_out);
+  TDX_REQUIRE(d.src_channels[0] + d.src_channels[1] + 1 == 6 || d.src_channels[0] + d.src_channels[1] + 1 == 12,
+              "conv_in: %d input channels; instantiated for 5 (decoder / latent models) or 11 (coarse model)",
+              d.src_channels[0] + d.src_channels[1]);
   TDX_REQUIRE(d.n_img >= 1 && d.height >= 1 && d.width >= 1, "conv_in: bad shape");
   const int ci = d.src_channels[0] + d.src_channels[1] + 1;
   TDX_REQUIRE(9 * ci * d.c_out * 4 <= 200 * 1024, "conv_in: weights (%d in, %d out) exceed shared memory", ci, d.c_out);
@@ -162,11 +199,17 @@ int conv_in_launch(const TdxConvInDesc& d, cudaStream_t stream) {
   const int smem = 9 * p.ci * p.cout * 4;
   int rc_prep = direct_prepare();
   if (rc_prep != TDX_OK) return rc_prep;
-  dim3 grid((d.height * d.width + 127) / 128, d.n_img);
+  dim3 grid((d.height * d.width + 32 * kConvInGroups - 1) / (32 * kConvInGroups), d.n_img);
   cudaLaunchConfig_t cfg;
   cudaLaunchAttribute attr[1];
   fill_launch_config(&cfg, attr, grid, dim3(128), smem, stream);
-  TDX_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_in_kernel, p));
+  switch (p.ci) {
+    case 6: TDX_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_in_kernel<6>, p)); break;
+    case 12: TDX_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_in_kernel<12>, p)); break;
+    default:
+      set_error("conv_in: %d input channels (incl. ones) not instantiated (6 or 12)", p.ci);
+      return TDX_E_UNSUPPORTED;
+  }
   return TDX_OK;
 }
 
@@ -189,56 +232,73 @@ __device__ __forceinline__ void sched_update(float x, float f, float x0p, float 
   x_new = __fadd_rn(t, __fmul_rn(k, __fsub_rn(x0, x0p)));
 }
 
+// Block = 128 threads = 32 pixels x 4 sub-threads; sub-thread s accumulates channel groups s, s+4, ... so four times as
+// many 16-byte loads are in flight; the partial sums are combined with two warp shuffles.  COUT = 1 (decoder) or 8.
+template <int COUT>
 __global__ void __launch_bounds__(128) conv_out_kernel(const ConvOutParams p) {
-  extern __shared__ float ws[];  // [tap][c][8]
+  extern __shared__ float ws[];  // [tap][c][COUT]
   const int C = p.C8 * 8;
-  for (int i = threadIdx.x; i < 9 * C * 8; i += blockDim.x) {
-    const int oc = i & 7, c = (i >> 3) % C, tap = i / (8 * C);
-    ws[i] = oc < p.cout ? p.weight[(oc * C + c) * 9 + tap] : 0.f;
-  }
+  for (int i = threadIdx.x; i < (9 * C * COUT) / 4; i += blockDim.x)
+    reinterpret_cast<float4*>(ws)[i] = __ldg(reinterpret_cast<const float4*>(p.weight) + i);
   pdl_launch_dependents();
   pdl_wait();
   __syncthreads();
   const int img = blockIdx.y;
-  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
-  if (pix >= p.H * p.W) return;
-  const int y = pix / p.W, x = pix % p.W;
+  const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
+  const int sub = lane >> 3;                                // 0..3
   const size_t plane = (size_t)p.H * p.W;
-  float acc[8];
+  for (int grp = 0; grp < kConvInGroups; ++grp) {
+    const int pix = (blockIdx.x * kConvInGroups + grp) * 32 + wq * 8 + (lane & 7);
+    const bool inb = pix < p.H * p.W;
+    const int y = inb ? pix / p.W : 0, x = inb ? pix % p.W : 0;
+    float acc[COUT];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-  for (int tap = 0; tap < 9; ++tap) {
-    const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
-    if (yy < 0 || yy >= p.H || xx < 0 || xx >= p.W) continue;
-    const uint4* src = p.x + (size_t)img * p.C8 * plane + (size_t)yy * p.W + xx;
-    for (int g = 0; g < p.C8; ++g) {
-      const uint4 u = __ldg(src + (size_t)g * plane);
-      float a[8];
-      unpack_bf16x2(u.x, a[0], a[1]); unpack_bf16x2(u.y, a[2], a[3]);
-      unpack_bf16x2(u.z, a[4], a[5]); unpack_bf16x2(u.w, a[6], a[7]);
-      const float4* w4 = reinterpret_cast<const float4*>(ws + (tap * C + g * 8) * 8);
+    for (int j = 0; j < COUT; ++j) acc[j] = 0.f;
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const float4 wa = w4[2 * e], wb = w4[2 * e + 1];
-        acc[0] = fmaf(wa.x, a[e], acc[0]); acc[1] = fmaf(wa.y, a[e], acc[1]);
-        acc[2] = fmaf(wa.z, a[e], acc[2]); acc[3] = fmaf(wa.w, a[e], acc[3]);
-        acc[4] = fmaf(wb.x, a[e], acc[4]); acc[5] = fmaf(wb.y, a[e], acc[5]);
-        acc[6] = fmaf(wb.z, a[e], acc[6]); acc[7] = fmaf(wb.w, a[e], acc[7]);
+    for (int tap = 0; tap < 9; ++tap) {
+      const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
+      if (!inb || yy < 0 || yy >= p.H || xx < 0 || xx >= p.W) continue;
+      const uint4* src = p.x + (size_t)img * p.C8 * plane + (size_t)yy * p.W + xx;
+      for (int g = sub; g < p.C8; g += 4) {
+        const uint4 u = __ldg(src + (size_t)g * plane);
+        float a[8];
+        unpack_bf16x2(u.x, a[0], a[1]); unpack_bf16x2(u.y, a[2], a[3]);
+        unpack_bf16x2(u.z, a[4], a[5]); unpack_bf16x2(u.w, a[6], a[7]);
+        const float* w = ws + (tap * C + g * 8) * COUT;
+        if (COUT == 1) {
+          const float4 wa = *reinterpret_cast<const float4*>(w), wb = *reinterpret_cast<const float4*>(w + 4);
+          acc[0] = fmaf(wa.x, a[0], acc[0]); acc[0] = fmaf(wa.y, a[1], acc[0]);
+          acc[0] = fmaf(wa.z, a[2], acc[0]); acc[0] = fmaf(wa.w, a[3], acc[0]);
+          acc[0] = fmaf(wb.x, a[4], acc[0]); acc[0] = fmaf(wb.y, a[5], acc[0]);
+          acc[0] = fmaf(wb.z, a[6], acc[0]); acc[0] = fmaf(wb.w, a[7], acc[0]);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+#pragma unroll
+            for (int j = 0; j < COUT; ++j) acc[j] = fmaf(w[e * COUT + j], a[e], acc[j]);
+          }
+        }
       }
     }
-  }
-  float cs = 0.f, co = 0.f, r = 0.f, k = 0.f;
-  if (p.coef) { cs = __ldg(p.coef); co = __ldg(p.coef + 1); r = __ldg(p.coef + 2); k = __ldg(p.coef + 3); }
 #pragma unroll
-  for (int oc = 0; oc < 8; ++oc) {
-    if (oc >= p.cout) break;
-    const size_t idx = ((size_t)img * p.cout + oc) * plane + pix;
-    if (p.model_out) p.model_out[idx] = acc[oc];
-    if (p.coef) {
-      float xn, x0;
-      sched_update(p.sample[idx], acc[oc], p.x0_prev[idx], cs, co, r, k, xn, x0);
-      p.sample[idx] = xn;
-      p.x0_prev[idx] = x0;
+    for (int j = 0; j < COUT; ++j) {
+      acc[j] += __shfl_xor_sync(0xffffffff, acc[j], 8);
+      acc[j] += __shfl_xor_sync(0xffffffff, acc[j], 16);
+    }
+    if (!inb || sub != 0) continue;
+    float cs = 0.f, co = 0.f, r = 0.f, k = 0.f;
+    if (p.coef) { cs = __ldg(p.coef); co = __ldg(p.coef + 1); r = __ldg(p.coef + 2); k = __ldg(p.coef + 3); }
+#pragma unroll
+    for (int oc = 0; oc < COUT; ++oc) {
+      if (oc >= p.cout) break;
+      const size_t idx = ((size_t)img * p.cout + oc) * plane + pix;
+      if (p.model_out) p.model_out[idx] = acc[oc];
+      if (p.coef) {
+        float xn, x0;
+        sched_update(p.sample[idx], acc[oc], p.x0_prev[idx], cs, co, r, k, xn, x0);
+        p.sample[idx] = xn;
+        p.x0_prev[idx] = x0;
+      }
     }
   }
 }
@@ -247,8 +307,10 @@ __global__ void __launch_bounds__(128) conv_out_kernel(const ConvOutParams p) {
 int direct_prepare() {
   static bool done = false;
   if (!done) {
-    TDX_CHECK_CUDA(cudaFuncSetAttribute(conv_in_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    TDX_CHECK_CUDA(cudaFuncSetAttribute(conv_out_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    TDX_CHECK_CUDA(cudaFuncSetAttribute(conv_in_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    TDX_CHECK_CUDA(cudaFuncSetAttribute(conv_in_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    TDX_CHECK_CUDA(cudaFuncSetAttribute(conv_out_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    TDX_CHECK_CUDA(cudaFuncSetAttribute(conv_out_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     done = true;
   }
   return TDX_OK;
@@ -276,14 +338,16 @@ int conv_out_launch(const TdxConvOutDesc& d, cudaStream_t stream) {
   p.coef = d.sched_coef;
   p.sample = d.sample;
   p.x0_prev = d.x0_prev;
-  const int smem = 9 * d.c_in * 8 * 4;
+  const int wout = d.c_out == 1 ? 1 : 8;
+  const int smem = 9 * d.c_in * wout * 4;
   int rc_prep = direct_prepare();
   if (rc_prep != TDX_OK) return rc_prep;
-  dim3 grid((d.height * d.width + 127) / 128, d.n_img);
+  dim3 grid((d.height * d.width + 32 * kConvInGroups - 1) / (32 * kConvInGroups), d.n_img);
   cudaLaunchConfig_t cfg;
   cudaLaunchAttribute attr[1];
   fill_launch_config(&cfg, attr, grid, dim3(128), smem, stream);
-  TDX_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_out_kernel, p));
+  if (wout == 1) TDX_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_out_kernel<1>, p));
+  else TDX_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_out_kernel<8>, p));
   return TDX_OK;
 }
 
@@ -298,10 +362,11 @@ struct EmbedParams {
   TdxEmbedBlock blocks[kMaxEmbedBlocks];
 };
 
+// One block per (U-Net block, image).  Weights are stored TRANSPOSED ([in][out]) so thread n's loads are coalesced and
+// independent; every block recomputes the 256-wide embedding (64 x 256 MACs) instead of paying a second launch.
 __global__ void __launch_bounds__(256) embed_kernel(const __grid_constant__ EmbedParams p) {
   __shared__ float pe[256];
   __shared__ float emb[1024];
-  __shared__ float cval[256];
   __shared__ float red[8];
   const int b = blockIdx.x, img = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -319,46 +384,68 @@ __global__ void __launch_bounds__(256) embed_kernel(const __grid_constant__ Embe
       pe[half + i] = cosf(yv) * 1.41421356237309515f;
     }
     __syncthreads();
-    for (int j = warp; j < p.E; j += 8) {
-      const float* wr = p.noise_weight + (size_t)j * p.noise_dims;
-      float s = 0.f;
-      for (int i = lane; i < p.noise_dims; i += 32) s = fmaf(wr[i], pe[i], s);
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffff, s, o);
-      if (lane == 0) emb[j] = mp_silu_precise(s);  // mp_sum of a single embed with weight [1] is the identity
+    for (int j = threadIdx.x; j < p.E; j += blockDim.x) {
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll 4
+      for (int i = 0; i < p.noise_dims; i += 4) {
+        s0 = fmaf(__ldg(p.noise_weight + (size_t)(i + 0) * p.E + j), pe[i + 0], s0);
+        s1 = fmaf(__ldg(p.noise_weight + (size_t)(i + 1) * p.E + j), pe[i + 1], s1);
+        s2 = fmaf(__ldg(p.noise_weight + (size_t)(i + 2) * p.E + j), pe[i + 2], s2);
+        s3 = fmaf(__ldg(p.noise_weight + (size_t)(i + 3) * p.E + j), pe[i + 3], s3);
+      }
+      emb[j] = mp_silu_precise((s0 + s1) + (s2 + s3));  // mp_sum of a single embed with weight [1] is the identity
     }
   }
   __syncthreads();
+  // c[n] = sum_j W^T[j][n] * emb[j] + 1: the 256 threads cover (n, quarter-of-j) so all of them stream weights
   const TdxEmbedBlock& blk = p.blocks[b];
-  float local_sq = 0.f;
-  for (int n = warp; n < blk.c_out; n += 8) {
-    const float* wr = blk.weight + (size_t)n * p.E;
-    float s = 0.f;
-    for (int j = lane; j < p.E; j += 32) s = fmaf(wr[j], emb[j], s);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffff, s, o);
-    s += 1.0f;
-    if (lane == 0) cval[n] = s;
-    local_sq += s * s;  // identical in all lanes
+  __shared__ float part[4][256];
+  const int parts = blk.c_out <= 64 ? 4 : (blk.c_out <= 128 ? 2 : 1);
+  const int n = threadIdx.x % (256 / parts), part_id = threadIdx.x / (256 / parts);
+  const int jlen = p.E / parts, j0 = part_id * jlen;
+  float acc = 0.f;
+  if (n < blk.c_out) {
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll 8
+    for (int j = j0; j < j0 + jlen; j += 4) {
+      s0 = fmaf(__ldg(blk.weight + (size_t)(j + 0) * blk.c_out + n), emb[j + 0], s0);
+      s1 = fmaf(__ldg(blk.weight + (size_t)(j + 1) * blk.c_out + n), emb[j + 1], s1);
+      s2 = fmaf(__ldg(blk.weight + (size_t)(j + 2) * blk.c_out + n), emb[j + 2], s2);
+      s3 = fmaf(__ldg(blk.weight + (size_t)(j + 3) * blk.c_out + n), emb[j + 3], s3);
+    }
+    acc = (s0 + s1) + (s2 + s3);
   }
-  if (lane == 0) red[warp] = local_sq;
+  part[part_id][n] = acc;
+  __syncthreads();
+  float c = 0.f;
+  const int nn = threadIdx.x;
+  if (nn < blk.c_out) {
+    c = 1.0f;
+    for (int q = 0; q < parts; ++q) c += part[q][nn];
+  }
+  float sq = c * c;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffff, sq, o);
+  if (lane == 0) red[warp] = sq;
   __syncthreads();
   float tot = 0.f;
 #pragma unroll
   for (int w = 0; w < 8; ++w) tot += red[w];
   const float inv = rsqrtf(tot / (float)blk.c_out + 1e-8f);
-  for (int n = threadIdx.x; n < blk.c_out; n += blockDim.x) blk.cvec[(size_t)img * blk.c_out + n] = cval[n] * inv;
+  if (nn < blk.c_out) blk.cvec[(size_t)img * blk.c_out + nn] = c * inv;
 }
 
 int embed_validate(const TdxEmbedDesc& d) {
   TDX_REQUIRE(d.n_blocks >= 1 && d.n_blocks <= kMaxEmbedBlocks, "embed: n_blocks=%d not in 1..%d", d.n_blocks,
               kMaxEmbedBlocks);
   TDX_REQUIRE(d.blocks, "embed: blocks is null");
-  TDX_REQUIRE(d.emb_channels >= 1 && d.emb_channels <= 1024, "embed: emb_channels=%d", d.emb_channels);
+  TDX_REQUIRE(d.emb_channels >= 4 && d.emb_channels <= 1024 && d.emb_channels % 4 == 0, "embed: emb_channels=%d",
+              d.emb_channels);
+  TDX_REQUIRE(d.emb_channels % 16 == 0, "embed: emb_channels must be a multiple of 16");
   TDX_REQUIRE(d.n_img >= 1, "embed: n_img");
   if (!d.emb_in) {
     TDX_REQUIRE(d.noise_labels && d.noise_weight && d.noise_freqs, "embed: noise path needs labels, weight, freqs");
-    TDX_REQUIRE(d.noise_dims >= 2 && d.noise_dims <= 256 && d.noise_dims % 2 == 0, "embed: noise_dims=%d",
+    TDX_REQUIRE(d.noise_dims >= 4 && d.noise_dims <= 256 && d.noise_dims % 4 == 0, "embed: noise_dims=%d",
                 d.noise_dims);
   }
   for (int b = 0; b < d.n_blocks; ++b)

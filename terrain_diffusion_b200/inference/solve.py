@@ -34,13 +34,15 @@ class DiffusionSolve:
         self.cond = torch.zeros((n, max(cc, 1), h, w), dtype=torch.float32, device=dev)
         self.x0_prev = torch.zeros_like(self.sample)
         self.prog = UNetProgram()
-        em = UNetEmitter(fw, n, h, w)
+        # the noise labels of all steps are known up front: ONE embed launch produces every step's modulation vectors
+        em = UNetEmitter(fw, n, h, w, cvec_sets=num_steps)
+        em.emit_embed(self.prog, labels=self.labels.reshape(-1))
         for i in range(num_steps):
             srcs = [(self.sample, cs, self.c_in[i:i + 1])]
             if cc > 0:
                 srcs.append((self.cond, cc, None))
-            em.emit(self.prog, srcs, labels=self.labels[i], model_out=None,
-                    sched=dict(coef=self.coef[i], sample=self.sample, x0_prev=self.x0_prev))
+            em.emit(self.prog, srcs, model_out=None,
+                    sched=dict(coef=self.coef[i], sample=self.sample, x0_prev=self.x0_prev), cvec_set=i)
         self.launches_per_solve = self.prog.n_launch
 
     @torch.no_grad()

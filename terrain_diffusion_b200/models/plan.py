@@ -135,20 +135,26 @@ class FoldedWeights:
         g: dict = {}
         self.g = g
         if self.noise_dims > 0:
-            g["noise_linear"] = effective_weight(sd["noise_linear.weight"]).contiguous()
+            g["noise_linear"] = effective_weight(sd["noise_linear.weight"]).t().contiguous()  # [in][out]
             if self.pos_emb:
                 g["noise_freqs"] = sd["noise_fourier.freqs"].contiguous()
         first = enc[0]
-        g["conv_in"] = effective_weight(sd[f"enc.{first['name']}.weight"]).contiguous()
+        w_in = effective_weight(sd[f"enc.{first['name']}.weight"])               # [cout][ci][3][3]
+        g["conv_in"] = w_in.permute(2, 3, 1, 0).reshape(9, w_in.shape[1], w_in.shape[0]).contiguous()  # [tap][ci][cout]
         out_gain = sd["out_gain"] if "out_gain" in sd else 1.0
-        g["conv_out"] = effective_weight(sd["out_conv.weight"], gain=out_gain).contiguous()
+        w_out = effective_weight(sd["out_conv.weight"], gain=out_gain)                  # [cout<=8][c][3][3]
+        wpad = 1 if w_out.shape[0] == 1 else 8
+        w_out8 = torch.zeros((wpad, w_out.shape[1], 3, 3), dtype=torch.float32, device=device)
+        w_out8[:w_out.shape[0]] = w_out
+        g["conv_out"] = w_out8.permute(2, 3, 1, 0).reshape(9, w_out.shape[1], wpad).contiguous()    # [tap][c][1|8]
         for side, blocks in (("enc", enc), ("dec", dec)):
             for b in blocks:
                 if b["kind"] != "block":
                     continue
                 p = f"{side}.{b['name']}."
                 if (p + "emb_linear.weight") in sd:
-                    g[p + "emb"] = effective_weight(sd[p + "emb_linear.weight"], gain=sd[p + "emb_gain"]).contiguous()
+                    g[p + "emb"] = effective_weight(sd[p + "emb_linear.weight"],
+                                                    gain=sd[p + "emb_gain"]).t().contiguous()  # [E][cout]
                 w0 = effective_weight(sd[p + "conv_res0.weight"])
                 w1 = effective_weight(sd[p + "conv_res1.weight"]) * self.w_res
                 ws = effective_weight(sd[p + "conv_skip.weight"]) if (p + "conv_skip.weight") in sd else None
@@ -180,6 +186,7 @@ class UNetProgram:
         self.handle = C.c_void_p()
         L.check(L.lib().tdx_program_create(C.byref(self.handle)))
         self.keep: list = []
+        self.arena: dict = {}
         self.n_igemm = 0
         self.n_launch = 0
 
@@ -209,7 +216,10 @@ class UNetProgram:
 class UNetEmitter:
     """Allocates the activation arena for (n, h, w) and appends the launches of one U-Net evaluation to a program."""
 
-    def __init__(self, fw: FoldedWeights, n: int, h: int, w: int):
+    def __init__(self, fw: FoldedWeights, n: int, h: int, w: int, cvec_sets: int = 1):
+        """cvec_sets: how many independent label sets (e.g. solver steps) share this arena; the modulation vectors of
+        all of them are produced by ONE embed launch (emit_embed) and selected per evaluation with `cvec_set`."""
+        self.cvec_sets = cvec_sets
         levels = len(fw.cfg.get("model_channel_mults") or [1, 2, 3, 4])
         need = 8 * 2 ** (levels - 1)
         if h % need or w % need:
@@ -226,7 +236,7 @@ class UNetEmitter:
 
     def cvec(self, key, c):
         if key not in self.cvecs:
-            self.cvecs[key] = torch.ones((self.n, c), dtype=torch.float32, device=self.dev)
+            self.cvecs[key] = torch.ones((self.cvec_sets * self.n, c), dtype=torch.float32, device=self.dev)
         return self.cvecs[key]
 
     # ------------------------------------------------------------------ helpers
@@ -289,41 +299,54 @@ class UNetEmitter:
         prog.n_igemm += 1
         prog.n_launch += 1
 
+    # ------------------------------------------------------------------ embedding / modulation vectors
+    def emit_embed(self, prog: UNetProgram, labels=None, emb_in=None):
+        """One launch producing the modulation vectors c_b of every block for `cvec_sets * n` label rows.
+        labels: fp32 [cvec_sets * n] device tensor, or emb_in: fp32 [cvec_sets * n, E] (host-computed embedding)."""
+        fw = self.fw
+        g = fw.g
+        seq = [("enc", b) for b in fw.enc] + [("dec", b) for b in fw.dec]
+        blocks = [(side, b) for side, b in seq if b["kind"] == "block" and f"{side}.{b['name']}.emb" in g]
+        if not blocks:
+            return
+        rows = self.cvec_sets * self.n
+        ed = L.TdxEmbedDesc()
+        arr = (L.TdxEmbedBlock * len(blocks))()
+        for i, (side, b) in enumerate(blocks):
+            key = f"{side}.{b['name']}."
+            arr[i].weight = g[key + "emb"].data_ptr()
+            arr[i].cvec = self.cvec(key, b["cout"]).data_ptr()
+            arr[i].c_out = b["cout"]
+        if emb_in is not None:
+            ed.emb_in = emb_in.data_ptr()
+        else:
+            if not (fw.pos_emb and fw.noise_dims > 0):
+                raise ValueError("this model needs a host-computed embedding (emb_in)")
+            assert labels.numel() == rows, (labels.shape, rows)
+            ed.noise_labels = labels.data_ptr()
+            ed.noise_weight = g["noise_linear"].data_ptr()
+            ed.noise_freqs = g["noise_freqs"].data_ptr()
+            ed.noise_dims = fw.noise_dims
+        ed.emb_channels = fw.emb_channels
+        ed.n_img = rows
+        ed.n_blocks = len(blocks)
+        ed.blocks = arr
+        L.check(L.lib().tdx_program_add_embed(prog.handle, C.byref(ed)))
+        prog.n_launch += 1
+        prog.keep.append((labels, emb_in))
+
+    def _cvec_ptr(self, key, c, cvec_set):
+        return self.cvec(key, c).data_ptr() + cvec_set * self.n * c * 4
+
     # ------------------------------------------------------------------ one U-Net evaluation
-    def emit(self, prog: UNetProgram, srcs, labels=None, emb_in=None, model_out=None, sched=None):
+    def emit(self, prog: UNetProgram, srcs, model_out=None, sched=None, cvec_set: int = 0):
         """srcs: [(tensor NCHW fp32/bf16, channels, scale_ptr_tensor or None)] (1 or 2 sources);
-        labels: fp32 [n] device tensor (noise-only models); emb_in: fp32 [n, E] device tensor (conditional models);
-        model_out: fp32 [n, Cout, h, w] or None; sched: None or dict(coef=tensor[4], sample=tensor, x0_prev=tensor)."""
+        model_out: fp32 [n, Cout, h, w] or None; sched: None or dict(coef=tensor[4], sample=tensor, x0_prev=tensor);
+        cvec_set: which label set's modulation vectors (see emit_embed) this evaluation uses."""
         fw = self.fw
         g = fw.g
         n, dev = self.n, self.dev
         seq = [("enc", i, b) for i, b in enumerate(fw.enc)] + [("dec", i, b) for i, b in enumerate(fw.dec)]
-
-        # ---- embedding / modulation vectors
-        blocks = [(side, b) for side, _, b in seq if b["kind"] == "block" and f"{side}.{b['name']}.emb" in g]
-        if blocks:
-            ed = L.TdxEmbedDesc()
-            arr = (L.TdxEmbedBlock * len(blocks))()
-            for i, (side, b) in enumerate(blocks):
-                key = f"{side}.{b['name']}."
-                arr[i].weight = g[key + "emb"].data_ptr()
-                arr[i].cvec = self.cvec(key, b["cout"]).data_ptr()
-                arr[i].c_out = b["cout"]
-            if emb_in is not None:
-                ed.emb_in = emb_in.data_ptr()
-            else:
-                if not (fw.pos_emb and fw.noise_dims > 0):
-                    raise ValueError("this model needs a host-computed embedding (emb_in)")
-                ed.noise_labels = labels.data_ptr()
-                ed.noise_weight = g["noise_linear"].data_ptr()
-                ed.noise_freqs = g["noise_freqs"].data_ptr()
-                ed.noise_dims = fw.noise_dims
-            ed.emb_channels = fw.emb_channels
-            ed.n_img = n
-            ed.n_blocks = len(blocks)
-            ed.blocks = arr
-            L.check(L.lib().tdx_program_add_embed(prog.handle, C.byref(ed)))
-            prog.n_launch += 1
 
         h, w = self.h, self.w
         cur = None
@@ -368,7 +391,7 @@ class UNetEmitter:
                 hbuf = self.act(key + "h", cout, h, w)
                 d = self._igemm(prog, [(a_in, cout, 9)], g[key + "res0"], cout, h, w)
                 d.epi_flags = L.EPI_EMB_SILU
-                d.cvec = self.cvec(key, cout).data_ptr()
+                d.cvec = self._cvec_ptr(key, cout, cvec_set)
                 self._set_out(d, 0, hbuf, L.OUT_RAW)
                 self._add_igemm(prog, d)
                 d = self._igemm(prog, [(hbuf, cout, 9)], g[key + "res1"], cout, h, w)
@@ -395,7 +418,7 @@ class UNetEmitter:
                     segs0 = [(cur["act"], b["cin"], 9)]
                 d = self._igemm(prog, segs0, g[key + "res0"], cout, h, w)
                 d.epi_flags = L.EPI_EMB_SILU
-                d.cvec = self.cvec(key, cout).data_ptr()
+                d.cvec = self._cvec_ptr(key, cout, cvec_set)
                 self._set_out(d, 0, hbuf, L.OUT_RAW)
                 self._add_igemm(prog, d)
                 if b.get("concat"):
@@ -427,4 +450,5 @@ class UNetEmitter:
             od.x0_prev = sched["x0_prev"].data_ptr()
         L.check(L.lib().tdx_program_add_conv_out(prog.handle, C.byref(od)))
         prog.n_launch += 1
-        prog.keep.append((self.arena, self.cvecs, fw, srcs, labels, emb_in, model_out, sched))
+        prog.keep.append((self.arena, self.cvecs, fw, srcs, model_out, sched))
+        prog.arena = self.arena

@@ -40,7 +40,7 @@ def main():
     out = m(x.cuda(), t.cuda(), [])
     torch.cuda.synchronize()
     prog, bufs = m._plans[("fwd", n, size, size, False)]
-    arena = prog.keep[0][0]
+    arena = prog.arena
     worst = 0.0
     for key, want in trace.items():
         got = from_nc8hw8(arena[key + ".raw"]).cpu()
