@@ -115,3 +115,29 @@ def sample_decoder_consistency_tiled(model, scheduler, cond_img: torch.Tensor, n
             for bi in range(b):
                 canvases[bi].accumulate(samples[bi].contiguous(), i0, j0, window)
     return torch.stack([cv.normalized(sigma_data) for cv in canvases]).to(dtype)
+
+
+@torch.no_grad()
+def sample_decoder_diffusion_sharded(model, scheduler, cond_img: torch.Tensor, noise: torch.Tensor, tile_size: int,
+                                     tile_stride: int, *, num_steps: int, tile_batch: int = 1, group=None):
+    """Multi-GPU form of sample_decoder_diffusion_tiled for ONE canvas (batch 1): every rank holds the full noise /
+    conditioning canvas (they are inputs), solves only its stripe of tile rows, and the overlap strips are exchanged
+    with the neighbours (inference/sharded.py).  Returns this rank's owned rows [C, rows, W] and their (lo, hi)."""
+    from .sharded import ShardedCanvas
+    b, c, h, w = noise.shape
+    assert b == 1, "one canvas per call"
+    device = noise.device
+    canvas = ShardedCanvas(c, h, w, tile_size, tile_stride, device, group=group)
+    tiles = canvas.my_tiles()
+    noise32, cond32 = noise.float(), cond_img.to(device).float()
+    group_n = max(1, int(tile_batch))
+    for g0 in range(0, len(tiles), group_n):
+        chunk = tiles[g0:g0 + group_n]
+        solve = get_diffusion_solve(model, scheduler, len(chunk), tile_size, tile_size, num_steps)
+        x = torch.cat([noise32[..., i0:i0 + tile_size, j0:j0 + tile_size] for (i0, j0) in chunk], dim=0)
+        cd = torch.cat([cond32[..., i0:i0 + tile_size, j0:j0 + tile_size] for (i0, j0) in chunk], dim=0)
+        out = solve.run(x, cd)
+        for t, (i0, j0) in enumerate(chunk):
+            canvas.add_tile(out[t].clone(), i0, j0)
+    canvas.finalize()
+    return canvas.normalized_owned(), (canvas.own_lo, canvas.own_hi)

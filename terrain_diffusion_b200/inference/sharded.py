@@ -1,0 +1,108 @@
+"""Multi-GPU canvas: tile rows striped across ranks, neighbour exchange of the overlap strips.
+
+The reference has no inference-time multi-GPU; this is the natural sharding of its tile loop: tiles within
+a phase are independent, so each rank solves the tile rows `tiling.shard_rows` gives it and owns the canvas rows from its
+first tile row to the next rank's first tile row.  Only a rank's LAST tile rows overhang into the next rank's pixels.
+The (sum x*w, sum w) partial sums of that strip go to the neighbour with one point-to-point message per boundary
+(torch.distributed send/recv: NCCL over NVLink on GPUs, gloo in the CPU tests) -- no collective in the data path.
+
+Bit-exactness: fp32 addition is order dependent, and the single-GPU order is row-major over tiles.  A
+rank therefore first INSTALLS the strip it receives from its upper neighbour and only then accumulates its own tiles
+in row-major order, so every pixel sees exactly the single-GPU sequence of additions.  The U-Net solves (the expensive
+part) are not serialised by this: tiles are solved first and buffered, `finalize()` runs the cheap blend chain.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+from .canvas import BlendCanvas
+from .tiling import shard_rows, tile_starts
+
+
+class ShardedCanvas:
+    def __init__(self, channels: int, height: int, width: int, tile_size: int, stride: int, device, group=None,
+                 canvas_factory=BlendCanvas, rank: int | None = None, world: int | None = None):
+        self.group = group
+        self.rank = dist.get_rank(group) if rank is None else rank
+        self.world = dist.get_world_size(group) if world is None else world
+        self.channels, self.height, self.width, self.tile = channels, height, width, tile_size
+        self.device = torch.device(device)
+        self.row_starts = tile_starts(height, tile_size, stride)
+        self.col_starts = tile_starts(width, tile_size, stride)
+        if len(self.row_starts) < self.world:
+            raise ValueError(f"{len(self.row_starts)} tile rows cannot be striped over {self.world} ranks")
+        self.rows = shard_rows(len(self.row_starts), self.world, self.rank)
+        first = [self.row_starts[shard_rows(len(self.row_starts), self.world, r)[0]] for r in range(self.world)]
+        first[0] = 0
+        self.bounds = first + [height]                       # rank r owns pixel rows [bounds[r], bounds[r+1])
+        self.own_lo, self.own_hi = self.bounds[self.rank], self.bounds[self.rank + 1]
+        self.cover_hi = min(height, self.row_starts[self.rows[-1]] + tile_size)   # how far this rank's tiles reach
+        if self.rank + 1 < self.world and self.cover_hi > self.bounds[self.rank + 2]:
+            raise ValueError("stripes are thinner than the tile overhang; use fewer ranks for this canvas")
+        # local canvas covers [own_lo, cover_hi)
+        self.local = canvas_factory(channels, self.cover_hi - self.own_lo, width, self.device,
+                                    origin=(self.own_lo, 0))
+        self._tiles: list = []
+
+    def my_tiles(self) -> list[tuple[int, int]]:
+        """Tile origins this rank must solve, row-major."""
+        return [(self.row_starts[r], j0) for r in self.rows for j0 in self.col_starts]
+
+    def add_tile(self, tile: torch.Tensor, i0: int, j0: int) -> None:
+        self._tiles.append((tile, i0, j0))
+
+    def _strip_rows(self) -> int:
+        return max(0, self.cover_hi - self.own_hi)
+
+    def finalize(self) -> None:
+        """Blend chain: install the upper neighbour's strip, accumulate own tiles (row-major), pass the overhang on."""
+        if self.rank > 0:
+            upper_cover = min(self.height,
+                              self.row_starts[shard_rows(len(self.row_starts), self.world, self.rank - 1)[-1]]
+                              + self.tile)
+            n = max(0, upper_cover - self.own_lo)
+            if n > 0:
+                buf = torch.empty((self.channels + 1, n, self.width), dtype=torch.float32, device=self.device)
+                dist.recv(buf, src=self._global(self.rank - 1), group=self.group)
+                self.local.val[:, :n] = buf[:-1]
+                self.local.wsum[:n] = buf[-1]
+        for tile, i0, j0 in sorted(self._tiles, key=lambda t: (t[1], t[2])):
+            self.local.accumulate(tile, i0, j0)
+        self._tiles.clear()
+        n = self._strip_rows()
+        if self.rank + 1 < self.world and n > 0:
+            lo = self.own_hi - self.own_lo
+            buf = torch.cat([self.local.val[:, lo:lo + n], self.local.wsum[None, lo:lo + n]], dim=0).contiguous()
+            dist.send(buf, dst=self._global(self.rank + 1), group=self.group)
+
+    def _global(self, r: int) -> int:
+        return dist.get_global_rank(self.group, r) if self.group is not None else r
+
+    def owned(self) -> tuple[torch.Tensor, torch.Tensor]:
+        """(sum x*w [C, rows, W], sum w [rows, W]) for the pixel rows this rank owns."""
+        n = self.own_hi - self.own_lo
+        return self.local.val[:, :n], self.local.wsum[:n]
+
+    def normalized_owned(self, divisor: float = 1.0) -> torch.Tensor:
+        val, w = self.owned()
+        out = val / w
+        return out if divisor == 1.0 else out / divisor
+
+    def gather(self, dst: int = 0):
+        """Full normalised canvas on rank `dst` (None elsewhere); for writers that want one array."""
+        part = self.normalized_owned().contiguous()
+        if self.rank == dst:
+            parts = [part]
+            for r in range(self.world):
+                if r == dst:
+                    continue
+                buf = torch.empty((self.channels, self.bounds[r + 1] - self.bounds[r], self.width),
+                                  dtype=torch.float32, device=self.device)
+                dist.recv(buf, src=self._global(r), group=self.group)
+                parts.append(buf)
+            order = [dst] + [r for r in range(self.world) if r != dst]
+            parts = [p for _, p in sorted(zip(order, parts), key=lambda t: t[0])]
+            return torch.cat(parts, dim=1)
+        dist.send(part, dst=self._global(dst), group=self.group)
+        return None
