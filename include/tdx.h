@@ -59,9 +59,10 @@ typedef struct TdxIgemmDesc {
   int32_t a_channels[3];   /* multiple of 64 */
   int32_t a_taps[3];       /* 9 (3x3, pad 1) or 1 (1x1) */
   int32_t n_seg;
-  /* B operand: packed bf16 weights [Cout/64 slices][stage = (segment, 64-channel chunk, tap)][8][64][8] */
+  /* B operand: packed bf16 weights [c_out/n_per_item slices][stage = (segment, 64-ch chunk, tap)][8][n_per_item][8] */
   const void* b_packed;
   int32_t c_out;           /* multiple of 64, <= 256 */
+  int32_t n_per_item;      /* output channels per work item = MMA N the weights were packed for (tdx_igemm_choose_n) */
   int32_t n_img, height, width;   /* output == input spatial size; multiples of 8 */
   /* epilogue */
   int32_t epi_flags;       /* TDX_EPI_* */
@@ -74,7 +75,11 @@ typedef struct TdxIgemmDesc {
   TdxOutSpec out[3];
 } TdxIgemmDesc;
 
-/* Bytes of packed B for a descriptor's segments. */
+/* Output channels per work item (64/128/192/256) the library prefers for this launch shape: balances the MMA issue
+ * floor (max(86, N/2) cycles per K=16 step), L2->SM traffic and CTA count.  Pack the weights for this value. */
+int tdx_igemm_choose_n(int32_t c_out, int32_t n_img, int32_t height, int32_t width, const int32_t* a_channels,
+                       const int32_t* a_taps, int32_t n_seg);
+/* Elements of packed B for a descriptor's segments. */
 int64_t tdx_igemm_packed_weight_elems(const int32_t* a_channels, const int32_t* a_taps, int32_t n_seg, int32_t c_out);
 /* One launch of the persistent tcgen05 kernel. */
 int tdx_igemm_run(const TdxIgemmDesc* desc, void* stream);

@@ -20,8 +20,8 @@ class TdxOutSpec(C.Structure):
 class TdxIgemmDesc(C.Structure):
     _fields_ = [
         ("a_ptr", C.c_void_p * 3), ("a_channels", C.c_int32 * 3), ("a_taps", C.c_int32 * 3), ("n_seg", C.c_int32),
-        ("b_packed", C.c_void_p), ("c_out", C.c_int32), ("n_img", C.c_int32), ("height", C.c_int32),
-        ("width", C.c_int32), ("epi_flags", C.c_int32), ("cvec", C.c_void_p), ("resid", C.c_void_p),
+        ("b_packed", C.c_void_p), ("c_out", C.c_int32), ("n_per_item", C.c_int32), ("n_img", C.c_int32),
+        ("height", C.c_int32), ("width", C.c_int32), ("epi_flags", C.c_int32), ("cvec", C.c_void_p), ("resid", C.c_void_p),
         ("resid_spatial", C.c_int32), ("resid_pnorm", C.c_int32), ("resid_scale", C.c_float), ("clip", C.c_float),
         ("out", TdxOutSpec * 3),
     ]
@@ -83,6 +83,9 @@ def _declare(l: C.CDLL) -> None:
     l.tdx_device_info.argtypes = [C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     l.tdx_igemm_packed_weight_elems.restype = C.c_int64
     l.tdx_igemm_packed_weight_elems.argtypes = [C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int32, C.c_int32]
+    l.tdx_igemm_choose_n.restype = C.c_int
+    l.tdx_igemm_choose_n.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32),
+                                     C.POINTER(C.c_int32), C.c_int32]
     l.tdx_igemm_run.restype = C.c_int
     l.tdx_igemm_run.argtypes = [C.POINTER(TdxIgemmDesc), C.c_void_p]
     l.tdx_abi_sizeof.restype = C.c_int
@@ -140,3 +143,10 @@ def check(rc: int) -> None:
 def current_stream_ptr() -> int:
     import torch
     return torch.cuda.current_stream().cuda_stream
+
+
+def igemm_choose_n(c_out: int, n_img: int, height: int, width: int, segs) -> int:
+    """segs: [(channels, taps)].  Output channels per work item the library prefers for this launch."""
+    ch = (C.c_int32 * 3)(*[c for c, _ in segs], *([0] * (3 - len(segs))))
+    tp = (C.c_int32 * 3)(*[t for _, t in segs], *([0] * (3 - len(segs))))
+    return int(lib().tdx_igemm_choose_n(c_out, n_img, height, width, ch, tp, len(segs)))

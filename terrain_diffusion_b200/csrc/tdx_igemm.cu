@@ -28,6 +28,8 @@
 //   N+1 overlap the tail of kernel N; griddepcontrol.wait guards everything that depends on earlier kernels.
 //
 // Reference math being replaced: models/mp_layers.py:201-221 (MPConv), models/unet_block.py:116-156 (UNetBlock).
+#include <stdlib.h>
+
 #include "tdx_common.h"
 #include "tdx_ptx.cuh"
 
@@ -38,14 +40,13 @@ constexpr int kPatchH = kTileH + 2, kPatchW = kTileW + 2;
 constexpr int kKcBytes = kPatchH * kPatchW * 16;  // one 8-channel plane of the halo patch: 2880 B
 constexpr int kAStageBytes = 8 * kKcBytes;        // 64 channels: 23040 B
 constexpr int kSA = 3;                            // A ring depth
-constexpr int kSB = 12;                           // B ring depth
-constexpr int kNCta = 64;                         // output channels per work item (MMA N)
-constexpr int kBStageBytes = kNCta * 128;         // 64 rows x 64 K x bf16 = 8 KB
-constexpr int kAccCols = 4 * kNCta;               // 4 partial accumulators
+constexpr int kMaxSB = 18;                        // B ring depth (max; also the largest resident weight set)
+constexpr int kAccCols = 256;                     // TMEM columns per accumulator buffer (2 buffers)
 constexpr int kEpiWarps = 8;
 constexpr int kThreads = 128 + 32 * kEpiWarps;
 constexpr int kMaxSplit = 4;
-constexpr int kSmemBytes = kSA * kAStageBytes + kSB * kBStageBytes + 8192;
+constexpr int kSmemMisc = 8192;                   // barriers, TMEM slot, pixel-norm statistics
+constexpr int kSmemBudget = 227 * 1024;
 
 struct IgemmParams {
   int nseg;
@@ -53,6 +54,10 @@ struct IgemmParams {
   int seg_taps[3];
   const __nv_bfloat16* B;
   int cout, nsplit;
+  int ncta;                   // output channels per work item = MMA N (64, 128, 192 or 256); cout = ncta * nsplit
+  int SB;                     // B ring depth
+  int b_stage_bytes;          // ncta * 128
+  int resident;               // the whole weight set of an item fits the ring: loaded once per CTA, reused by every item
   int H, W, nimg, tiles_x, tiles_y, num_items;
   int stages_per_item;
   int epi;
@@ -144,19 +149,12 @@ __device__ __forceinline__ void store_group(const OutCtx& o, int group, const fl
   }
 }
 
-// Sum of the four partial accumulators for 32 columns of this warp's lane quadrant.
 __device__ __forceinline__ void load_acc32(uint32_t taddr, float (&v)[32]) {
-  uint32_t r0[32], r1[32];
-  tmem_ld32(taddr, r0);
-  tmem_ld32(taddr + kNCta, r1);
+  uint32_t r[32];
+  tmem_ld32(taddr, r);
   tmem_ld_wait();
 #pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r0[i]) + __uint_as_float(r1[i]);
-  tmem_ld32(taddr + 2 * kNCta, r0);
-  tmem_ld32(taddr + 3 * kNCta, r1);
-  tmem_ld_wait();
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] += __uint_as_float(r0[i]) + __uint_as_float(r1[i]);
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -165,12 +163,12 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CU
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* a_ring = smem;
   uint8_t* b_ring = smem + kSA * kAStageBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(b_ring + kSB * kBStageBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(b_ring + p.SB * p.b_stage_bytes);
   uint64_t* a_full = bars;
   uint64_t* a_empty = a_full + kSA;
   uint64_t* b_full = a_empty + kSA;
-  uint64_t* b_empty = b_full + kSB;
-  uint64_t* t_full = b_empty + kSB;
+  uint64_t* b_empty = b_full + kMaxSB;
+  uint64_t* t_full = b_empty + kMaxSB;
   uint64_t* t_empty = t_full + 2;
   uint64_t* x_full = t_empty + 2;                                     // [2] cluster statistics barriers
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(x_full + 2);
@@ -191,7 +189,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CU
       mbar_init(&a_full[i], 1);
       mbar_init(&a_empty[i], 1);
     }
-    for (int i = 0; i < kSB; ++i) {
+    for (int i = 0; i < p.SB; ++i) {
       mbar_init(&b_full[i], 1);
       mbar_init(&b_empty[i], 1);
     }
@@ -244,27 +242,38 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CU
     int sb = 0;
     uint32_t ph = 0;
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
-      const int split = item % p.nsplit;
-      const uint8_t* bsrc = reinterpret_cast<const uint8_t*>(p.B) + (size_t)split * p.stages_per_item * kBStageBytes;
+      const int split = item % p.nsplit;   // constant per CTA: gridDim.x is a multiple of nsplit
+      const uint8_t* bsrc = reinterpret_cast<const uint8_t*>(p.B) + (size_t)split * p.stages_per_item * p.b_stage_bytes;
       for (int ks = 0; ks < p.stages_per_item; ++ks) {
-        mbar_wait(&b_empty[sb], ph ^ 1, 200 + sb);
+        if (!p.resident) mbar_wait(&b_empty[sb], ph ^ 1, 200 + sb);
         if (elect_one()) {
           if (p.dbg & 2) {
             mbar_arrive(&b_full[sb]);
           } else {
-            mbar_expect_tx(&b_full[sb], kBStageBytes);
-            bulk_load_1d(bsrc + (size_t)ks * kBStageBytes, &b_full[sb], b_ring + sb * kBStageBytes, kBStageBytes);
+            mbar_expect_tx(&b_full[sb], p.b_stage_bytes);
+            bulk_load_1d(bsrc + (size_t)ks * p.b_stage_bytes, &b_full[sb], b_ring + sb * p.b_stage_bytes,
+                         p.b_stage_bytes);
           }
         }
         __syncwarp();
-        if (++sb == kSB) { sb = 0; ph ^= 1; }
+        if (++sb == p.SB) { sb = 0; ph ^= 1; }
       }
+      if (p.resident) break;   // the ring now holds this CTA's whole weight slice for every later item
     }
   } else if (warp == 2) {
     // ------------------------------------------------------------------ MMA issuer (one elected lane issues)
-    const uint32_t idesc = make_idesc_bf16(128, kNCta);
-    constexpr uint32_t b_lbo = kNCta * 16;
+    const uint32_t idesc = make_idesc_bf16(128, p.ncta);
+    const uint32_t b_lbo = p.ncta * 16;
     const uint32_t a_sbo = (p.dbg & 1) ? 128 : kPatchW * 16;
+    // Descriptors are built as (constant upper bits) | (start address >> 4); per MMA only the 14-bit address field
+    // changes, by compile-time offsets for the tap (r*10 + c pixels) and the K step (2 planes of 2880 B), so the issue
+    // loop has no dependent address arithmetic between UTCHMMAs.
+    const uint64_t a_hi = make_smem_desc(0, kKcBytes, a_sbo);
+    const uint64_t b_hi = make_smem_desc(0, b_lbo, 128);
+    // (in a cluster launch the shared-window address carries the CTA rank in its upper bits: keep the 14-bit field only)
+    const uint32_t a_ring16 = (smem_u32(a_ring) >> 4) & 0x3FFF, b_ring16 = (smem_u32(b_ring) >> 4) & 0x3FFF;
+    const uint32_t b_stage16 = p.b_stage_bytes >> 4, b_kstep16 = (2 * b_lbo) >> 4;
+    constexpr uint32_t a_kstep16 = (2 * kKcBytes) >> 4;
     int sa = 0, sb = 0;
     uint32_t pha = 0, phb = 0;
     int it = 0;
@@ -275,6 +284,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CU
       tc_fence_after();
       if (lane == 0) TDX_TRACE(1, it);
       const uint32_t d_tmem = tmem_base + acc * kAccCols;
+      const bool steady = p.resident && it > 0;   // weights already in the ring: no per-stage handshakes
       uint32_t accumulate = 0;
       for (int seg = 0; seg < p.nseg; ++seg) {
         const int taps = p.seg_taps[seg];
@@ -282,27 +292,46 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CU
           mbar_wait(&a_full[sa], pha, 400 + sa);
           tc_fence_after();
           if (lane == 0 && seg == 0 && ch == 0) TDX_TRACE(2, it);
-          const uint32_t a_base = smem_u32(a_ring + sa * kAStageBytes);
-          for (int tap = 0; tap < taps; ++tap) {
-            const int r = taps == 9 ? tap / 3 : 1;
-            const int c = taps == 9 ? tap % 3 : 1;
-            mbar_wait(&b_full[sb], phb, 500 + sb);
-            tc_fence_after();
-            const uint32_t b_base = smem_u32(b_ring + sb * kBStageBytes);
-            const uint32_t a_tap = a_base + (r * kPatchW + c) * 16;
+          const uint32_t a16 = a_ring16 + sa * (kAStageBytes >> 4);
+          if (steady && taps == 9) {
+            // ---- 36 MMAs back to back
+            const uint32_t b16 = b_ring16 + sb * b_stage16;
             if (elect_one()) {
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                // K step j accumulates into partial accumulator j: no MMA depends on its predecessor
-                const uint64_t adesc = make_smem_desc(a_tap + 2 * j * kKcBytes, kKcBytes, a_sbo);
-                const uint64_t bdesc = make_smem_desc(b_base + 2 * j * b_lbo, b_lbo, 128);
-                umma_bf16(d_tmem + j * kNCta, adesc, bdesc, idesc, accumulate);
+              for (int tap = 0; tap < 9; ++tap) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const uint64_t adesc = a_hi | (uint64_t)(a16 + (tap / 3) * kPatchW + (tap % 3) + j * a_kstep16);
+                  const uint64_t bdesc = b_hi | (uint64_t)(b16 + tap * b_stage16 + j * b_kstep16);
+                  umma_bf16(d_tmem, adesc, bdesc, idesc, (accumulate | tap | j) ? 1u : 0u);
+                }
               }
-              umma_commit(&b_empty[sb]);
             }
             __syncwarp();
             accumulate = 1;
-            if (++sb == kSB) { sb = 0; phb ^= 1; }
+            sb += 9;   // resident ring: SB == stages_per_item, a chunk's 9 stages never wrap
+            if (sb >= p.SB) { sb -= p.SB; phb ^= 1; }
+          } else {
+            for (int tap = 0; tap < taps; ++tap) {
+              const uint32_t tapoff = taps == 9 ? (uint32_t)((tap / 3) * kPatchW + (tap % 3)) : (uint32_t)(kPatchW + 1);
+              const uint32_t b16 = b_ring16 + sb * b_stage16;
+              if (!steady) {
+                mbar_wait(&b_full[sb], phb, 500 + sb);
+                tc_fence_after();
+              }
+              if (elect_one()) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const uint64_t adesc = a_hi | (uint64_t)(a16 + tapoff + j * a_kstep16);
+                  const uint64_t bdesc = b_hi | (uint64_t)(b16 + j * b_kstep16);
+                  umma_bf16(d_tmem, adesc, bdesc, idesc, (accumulate | j) ? 1u : 0u);
+                }
+                if (!p.resident) umma_commit(&b_empty[sb]);
+              }
+              __syncwarp();
+              accumulate = 1;
+              if (++sb == p.SB) { sb = 0; phb ^= 1; }
+            }
           }
           if (elect_one()) umma_commit(&a_empty[sa]);
           __syncwarp();
@@ -313,15 +342,16 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CU
       __syncwarp();
       if (lane == 0) TDX_TRACE(3, it);
     }
-  } else if (warp >= 4) {
+  } else if (warp >= 4 && !(p.dbg & 8)) {
     // ------------------------------------------------------------------ epilogue (TMEM -> registers -> global)
-    // warp w and w+4 share TMEM lane quadrant (w & 3); `half` selects which 32 of the item's 64 columns a warp owns.
+    // warp w and w+4 share TMEM lane quadrant (w & 3); the item's 32-column chunks alternate between the two.
     pdl_wait();  // residual / cvec come from earlier kernels; our stores must not race their readers
     const int q = warp & 3;
     const int half = (warp - 4) >> 2;
     const int m = q * 32 + lane;
     const int y = m >> 3, x = m & 7;
     const int C8 = p.cout >> 3;
+    const int nchunks = p.ncta >> 5;
     const bool need_norm = (p.epi & TDX_EPI_PNORM) || p.out[0].kind == TDX_OUT_PNORM_SILU ||
                            p.out[1].kind == TDX_OUT_PNORM_SILU || p.out[2].kind == TDX_OUT_PNORM_SILU;
     const bool fast_res0 = (p.epi == TDX_EPI_EMB_SILU) && p.clip <= 0.f && p.out[0].kind == TDX_OUT_RAW &&
@@ -336,27 +366,28 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CU
       decode_item(p, item, split, img, Y0, X0);
       const int Y = Y0 + y, X = X0 + x;
       const bool valid = (Y < p.H) && (X < p.W);
-      const int ch0 = split * kNCta + half * 32;          // first output channel this warp produces
-      const int g0 = ch0 >> 3;                            // its first channel group
-      const uint32_t taddr = tmem_base + acc * kAccCols + half * 32 + ((uint32_t)(q * 32) << 16);
-      const float* cv = p.cvec ? p.cvec + (size_t)img * p.cout + ch0 : nullptr;
+      const int chbase = split * p.ncta;                  // first output channel of this item
+      const uint32_t taddr = tmem_base + acc * kAccCols + ((uint32_t)(q * 32) << 16);
+      const float* cvb = p.cvec ? p.cvec + (size_t)img * p.cout + chbase : nullptr;
 
       if (fast_res0) {
         // ---------------- res0: v = mp_silu(acc * c) -> one bf16 output (the common case: half of all launches)
         const size_t oplane = (size_t)p.H * p.W;
-        uint4* optr = reinterpret_cast<uint4*>(p.out[0].ptr) + ((size_t)img * C8 + g0) * oplane + (size_t)Y * p.W + X;
-        float4 c4[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) c4[i] = __ldg(reinterpret_cast<const float4*>(cv) + i);
+        uint4* obase = reinterpret_cast<uint4*>(p.out[0].ptr) + ((size_t)img * C8 + (chbase >> 3)) * oplane +
+                       (size_t)Y * p.W + X;
         if (warp == 4 && lane == 0) TDX_TRACE(4, it);
         mbar_wait(&t_full[acc], accph, 600 + acc);
         tc_fence_after();
         if (warp == 4 && lane == 0) TDX_TRACE(5, it);
-        if (!(p.dbg & 4)) {
+        for (int ck = half; ck < ((p.dbg & 4) ? 0 : nchunks); ck += 2) {
+          float4 c4[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) c4[i] = __ldg(reinterpret_cast<const float4*>(cvb + ck * 32) + i);
           float v[32];
           __syncwarp();
-          load_acc32(taddr, v);
+          load_acc32(taddr + ck * 32, v);
           if (valid) {
+            uint4* optr = obase + (size_t)(ck * 4) * oplane;
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
               const float4 ca = c4[2 * g], cb = c4[2 * g + 1];
@@ -380,7 +411,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CU
         }
       } else {
         // ---------------- general: residual mp_sum (+pixel-norm of the residual), clip, pixel-norm, up to 3 outputs
-        const uint4* rptr = nullptr;
+        const uint4* rbase = nullptr;
         size_t rplane = 0;
         float rscale = p.resid_scale;
         if ((p.epi & TDX_EPI_RESID) && valid) {
@@ -388,9 +419,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CU
           if (p.resid_spatial == TDX_SP_UP2) { Hr = p.H >> 1; Wr = p.W >> 1; Yr = Y >> 1; Xr = X >> 1; }
           else if (p.resid_spatial == TDX_SP_DOWN2) { Hr = p.H << 1; Wr = p.W << 1; Yr = Y << 1; Xr = X << 1; }
           rplane = (size_t)Hr * Wr;
-          const uint4* rbase = p.resid + ((size_t)img * C8) * rplane + (size_t)Yr * Wr + Xr;
+          rbase = p.resid + ((size_t)img * C8) * rplane + (size_t)Yr * Wr + Xr;
           if (p.resid_pnorm) {
-            // the residual's pixel-norm runs over ALL Cout channels (every split reads them; L2-resident)
+            // the residual's pixel-norm runs over ALL Cout channels (every item reads them; L2-resident)
             float ss = 0.f;
             for (int g = 0; g < C8; ++g) {
               uint4 u = __ldg(rbase + g * rplane);
@@ -402,7 +433,6 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CU
             }
             rscale = p.resid_scale / (1e-4f + sqrtf(ss / (float)p.cout));
           }
-          rptr = rbase + (size_t)g0 * rplane;
         }
         OutCtx oc[3];
 #pragma unroll
@@ -420,7 +450,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CU
           }
           oc[o].plane = (size_t)Ho * Wo;
           oc[o].Wo = Wo;
-          oc[o].ptr = reinterpret_cast<uint4*>(os.ptr) + ((size_t)img * C8 + g0) * oc[o].plane + (size_t)Yo * Wo + Xo;
+          oc[o].ptr = reinterpret_cast<uint4*>(os.ptr) + ((size_t)img * C8 + (chbase >> 3)) * oc[o].plane +
+                      (size_t)Yo * Wo + Xo;
           oc[o].hs = 0.5f * os.scale;
           oc[o].hsk = 0.5f * os.scale * (1.0f / 0.596f);
         }
@@ -430,14 +461,14 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CU
         tc_fence_after();
         if (warp == 4 && lane == 0) TDX_TRACE(5, it);
 
-        if (!(p.dbg & 4)) {
-          float v[32];
+        // v = accumulator chunk `ck` after emb-silu / residual / clip (everything that precedes the pixel-norm)
+        auto compute_v = [&](int ck, float (&v)[32]) {
           __syncwarp();
-          load_acc32(taddr, v);
+          load_acc32(taddr + ck * 32, v);
           if (p.epi & TDX_EPI_EMB_SILU) {
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
-              float4 c4 = __ldg(reinterpret_cast<const float4*>(cv + i));
+              float4 c4 = __ldg(reinterpret_cast<const float4*>(cvb + ck * 32 + i));
               v[i + 0] = mp_silu_f(v[i + 0] * c4.x);
               v[i + 1] = mp_silu_f(v[i + 1] * c4.y);
               v[i + 2] = mp_silu_f(v[i + 2] * c4.z);
@@ -445,6 +476,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CU
             }
           }
           if (p.epi & TDX_EPI_RESID) {
+            const uint4* rptr = rbase + (size_t)((chbase >> 3) + ck * 4) * rplane;
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
               uint4 u = valid ? __ldg(rptr + (size_t)g * rplane) : make_uint4(0, 0, 0, 0);
@@ -461,43 +493,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CU
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = fminf(fmaxf(v[i], -p.clip), p.clip);
           }
-          float inv = 1.f;
-          if (need_norm) {
-            float sumsq = 0.f;
-#pragma unroll
-            for (int i = 0; i < 32; ++i) sumsq = fmaf(v[i], v[i], sumsq);
-            // (1) combine the two 32-column halves of this CTA (warps w and w+4 own the same pixels)
-            ssq[half * 128 + m] = sumsq;
-            named_bar_sync(1 + q, 64);
-            float tot = ssq[m] + ssq[128 + m];
-            if (p.cluster_stats) {
-              // (2) combine the Cout/64 CTAs of this M tile through distributed shared memory
-              const int par = it & 1;
-              if (half == 0) {
-                for (uint32_t r = 0; r < (uint32_t)p.nsplit; ++r) {
-                  if (r == my_rank) continue;
-                  st_cluster_f32(map_to_cta(smem_u32(&xstat[(par * kMaxSplit + my_rank) * 128 + m]), r), tot);
-                  mbar_arrive_cluster(map_to_cta(smem_u32(&x_full[par]), r));
-                }
-                const uint32_t xph = (it >> 1) & 1;
-                if (!mbar_try_wait_cluster(&x_full[par], xph)) {
-                  long long t0 = clock64();
-                  while (!mbar_try_wait_cluster(&x_full[par], xph)) {
-                    if (clock64() - t0 > TDX_WAIT_LIMIT) {
-                      printf("tdx: cluster statistics wait timeout block=%d\n", (int)blockIdx.x);
-                      __trap();
-                    }
-                  }
-                }
-                for (uint32_t r = 0; r < (uint32_t)p.nsplit; ++r)
-                  if (r != my_rank) tot += xstat[(par * kMaxSplit + r) * 128 + m];
-                stot[m] = tot;
-              }
-              named_bar_sync(5 + q, 64);
-              tot = stot[m];
-            }
-            inv = 1.0f / (1e-4f + sqrtf(tot / (float)p.cout));
-          }
+        };
+        auto emit_v = [&](int ck, float (&v)[32], float inv) {
           if (p.epi & TDX_EPI_PNORM) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] *= inv;
@@ -512,7 +509,73 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CU
               hsk = 0.5f * sc * (1.0f / 0.596f);
             }
 #pragma unroll
-            for (int g = 0; g < 4; ++g) store_group(oc[o], g, v + g * 8, hs, hsk);
+            for (int g = 0; g < 4; ++g) store_group(oc[o], ck * 4 + g, v + g * 8, hs, hsk);
+          }
+        };
+        // per-pixel sum of squares over ALL Cout channels -> 1 / (eps + rms)
+        auto finish_norm = [&](float sumsq) -> float {
+          // (1) combine the two warps that own the same pixels (named barrier per lane quadrant)
+          ssq[half * 128 + m] = sumsq;
+          named_bar_sync(1 + q, 64);
+          float tot = ssq[m] + ssq[128 + m];
+          if (p.cluster_stats) {
+            // (2) combine the Cout/ncta CTAs of this M tile through distributed shared memory
+            const int par = it & 1;
+            if (half == 0) {
+              for (uint32_t r = 0; r < (uint32_t)p.nsplit; ++r) {
+                if (r == my_rank) continue;
+                st_cluster_f32(map_to_cta(smem_u32(&xstat[(par * kMaxSplit + my_rank) * 128 + m]), r), tot);
+                mbar_arrive_cluster(map_to_cta(smem_u32(&x_full[par]), r));
+              }
+              const uint32_t xph = (it >> 1) & 1;
+              if (!mbar_try_wait_cluster(&x_full[par], xph)) {
+                long long t0 = clock64();
+                while (!mbar_try_wait_cluster(&x_full[par], xph)) {
+                  if (clock64() - t0 > TDX_WAIT_LIMIT) {
+                    printf("tdx: cluster statistics wait timeout block=%d\n", (int)blockIdx.x);
+                    __trap();
+                  }
+                }
+              }
+              for (uint32_t r = 0; r < (uint32_t)p.nsplit; ++r)
+                if (r != my_rank) tot += xstat[(par * kMaxSplit + r) * 128 + m];
+              stot[m] = tot;
+            }
+            named_bar_sync(5 + q, 64);
+            tot = stot[m];
+          }
+          return 1.0f / (1e-4f + sqrtf(tot / (float)p.cout));
+        };
+
+        if (!(p.dbg & 4)) {
+          float v[32];
+          if (!need_norm) {
+            for (int ck = half; ck < nchunks; ck += 2) {
+              compute_v(ck, v);
+              emit_v(ck, v, 1.f);
+            }
+          } else if (nchunks <= 2) {
+            // one chunk per warp: keep it in registers across the statistics exchange
+            float sumsq = 0.f;
+            if (half < nchunks) {
+              compute_v(half, v);
+#pragma unroll
+              for (int i = 0; i < 32; ++i) sumsq = fmaf(v[i], v[i], sumsq);
+            }
+            const float inv = finish_norm(sumsq);
+            if (half < nchunks) emit_v(half, v, inv);
+          } else {
+            float sumsq = 0.f;
+            for (int ck = half; ck < nchunks; ck += 2) {
+              compute_v(ck, v);
+#pragma unroll
+              for (int i = 0; i < 32; ++i) sumsq = fmaf(v[i], v[i], sumsq);
+            }
+            const float inv = finish_norm(sumsq);
+            for (int ck = half; ck < nchunks; ck += 2) {
+              compute_v(ck, v);
+              emit_v(ck, v, inv);
+            }
           }
         }
       }
@@ -539,7 +602,7 @@ static int g_dbg_flags = 0;
 int igemm_prepare() {
   static bool attr_set = false;
   if (!attr_set) {
-    TDX_CHECK_CUDA(cudaFuncSetAttribute(igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    TDX_CHECK_CUDA(cudaFuncSetAttribute(igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
     attr_set = true;
   }
   return TDX_OK;
@@ -552,25 +615,67 @@ static bool needs_norm(const TdxIgemmDesc& d) {
   return false;
 }
 
+// Choose the output-channel width of a work item (MMA N).  Model (cycles), from measurements on B200:
+//   * an SS-mode M=128 K=16 tcgen05.mma costs max(86, N/2) cycles (tools/probe/mma_probe.cu);
+//   * L2 -> SM delivers ~2.8 KB/clk chip-wide; per item the A patches (23 KB per 64 input channels) and, unless the
+//     item's whole weight slice fits the B ring ("resident": loaded once per CTA), the weights (N*128 B per stage).
+static void choose_item_shape(int cout, int tiles, int stages, int chunks, int forced, int* ncta_out,
+                              int* resident_out, int* sb_out) {
+  if (!forced && getenv("TDX_IGEMM_N")) forced = atoi(getenv("TDX_IGEMM_N"));
+  if (forced && (forced > cout || cout % forced)) forced = 0;
+  const int ring_budget = kSmemBudget - kSA * kAStageBytes - kSmemMisc;
+  double best = 1e30;
+  int best_n = 64, best_res = 0, best_sb = 2;
+  for (int n = 64; n <= 256 && n <= cout; n += 64) {
+    if (cout % n) continue;
+    if (forced && n != forced) continue;
+    const int stage_bytes = n * 128;
+    const int resident = (stages * stage_bytes <= ring_budget && stages <= kMaxSB) ? 1 : 0;
+    int sb = resident ? stages : ring_budget / stage_bytes;
+    if (sb > kMaxSB) sb = kMaxSB;
+    if (sb < 2) continue;
+    const int nsplit = cout / n;
+    const long items = (long)tiles * nsplit;
+    int grid = items < sm_count() ? (int)items : sm_count();
+    grid -= grid % nsplit;
+    const double rounds = (double)((items + grid - 1) / grid);
+    const double mma = rounds * stages * 4.0 * (n / 2.0 > 86.0 ? n / 2.0 : 86.0);
+    const double a_bytes = (double)items * chunks * kAStageBytes;
+    const double b_bytes = resident ? (double)grid * stages * stage_bytes : (double)items * stages * stage_bytes;
+    const double l2 = (a_bytes + b_bytes) / 2800.0;
+    const double epi = rounds * (n / 32) * 150.0 / 2.0;
+    const double t = (mma > l2 ? mma : l2) + epi + 4000.0;
+    if (t < best) { best = t; best_n = n; best_res = resident; best_sb = sb; }
+  }
+  *ncta_out = best_n;
+  *resident_out = best_res;
+  *sb_out = best_sb;
+}
+
 int igemm_launch(const TdxIgemmDesc& d, const CUtensorMap* tms, cudaStream_t stream) {
   IgemmParams p;
   memset(&p, 0, sizeof(p));
   p.nseg = d.n_seg;
   p.stages_per_item = 0;
+  int chunks = 0;
   for (int s = 0; s < d.n_seg; ++s) {
     p.seg_chunks[s] = d.a_channels[s] / 64;
     p.seg_taps[s] = d.a_taps[s];
     p.stages_per_item += p.seg_chunks[s] * p.seg_taps[s];
+    chunks += p.seg_chunks[s];
   }
   p.B = reinterpret_cast<const __nv_bfloat16*>(d.b_packed);
   p.cout = d.c_out;
-  p.nsplit = d.c_out / kNCta;
   p.H = d.height;
   p.W = d.width;
   p.nimg = d.n_img;
   p.tiles_x = (d.width + kTileW - 1) / kTileW;
   p.tiles_y = (d.height + kTileH - 1) / kTileH;
-  p.num_items = p.tiles_x * p.tiles_y * d.n_img * p.nsplit;
+  const int tiles = p.tiles_x * p.tiles_y * d.n_img;
+  choose_item_shape(d.c_out, tiles, p.stages_per_item, chunks, d.n_per_item, &p.ncta, &p.resident, &p.SB);
+  p.nsplit = d.c_out / p.ncta;
+  p.b_stage_bytes = p.ncta * 128;
+  p.num_items = tiles * p.nsplit;
   p.epi = d.epi_flags;
   p.cluster_stats = (needs_norm(d) && p.nsplit > 1) ? 1 : 0;
   p.cvec = d.cvec;
@@ -585,15 +690,16 @@ int igemm_launch(const TdxIgemmDesc& d, const CUtensorMap* tms, cudaStream_t str
 
   int rc_prep = igemm_prepare();
   if (rc_prep != TDX_OK) return rc_prep;
-  // grid: one CTA per SM at most, a multiple of nsplit so the splits of an M tile always run side by side
+  // grid: one CTA per SM at most, a multiple of nsplit so the slices of an M tile always run side by side
   int grid = p.num_items < sm_count() ? p.num_items : sm_count();
   grid -= grid % p.nsplit;
+  const int smem = kSA * kAStageBytes + p.SB * p.b_stage_bytes + kSmemMisc;
   const CUtensorMap& t0 = tms[0];
   const CUtensorMap& t1 = tms[d.n_seg > 1 ? 1 : 0];
   const CUtensorMap& t2 = tms[d.n_seg > 2 ? 2 : 0];
   cudaLaunchConfig_t cfg;
   cudaLaunchAttribute attr[2];
-  fill_launch_config(&cfg, attr, dim3(grid), dim3(kThreads), kSmemBytes, stream);
+  fill_launch_config(&cfg, attr, dim3(grid), dim3(kThreads), smem < 120 * 1024 ? 120 * 1024 : smem, stream);
   if (p.cluster_stats) {
     attr[cfg.numAttrs].id = cudaLaunchAttributeClusterDimension;
     attr[cfg.numAttrs].val.clusterDim.x = p.nsplit;
@@ -617,6 +723,9 @@ int igemm_validate(const TdxIgemmDesc& d) {
   TDX_REQUIRE(d.b_packed != nullptr, "igemm: b_packed is null");
   TDX_REQUIRE(d.c_out >= 64 && d.c_out <= 64 * kMaxSplit && d.c_out % 64 == 0,
               "igemm: c_out=%d must be a multiple of 64 <= %d", d.c_out, 64 * kMaxSplit);
+  TDX_REQUIRE(d.n_per_item >= 64 && d.n_per_item <= 256 && d.n_per_item % 64 == 0 && d.c_out % d.n_per_item == 0,
+              "igemm: n_per_item=%d must be 64/128/192/256 and divide c_out=%d (use tdx_igemm_choose_n)", d.n_per_item,
+              d.c_out);
   TDX_REQUIRE(d.n_img >= 1 && d.height >= 8 && d.width >= 8 && d.height % 8 == 0 && d.width % 8 == 0,
               "igemm: bad shape n=%d h=%d w=%d (h, w multiples of 8)", d.n_img, d.height, d.width);
   if (d.epi_flags & TDX_EPI_EMB_SILU) TDX_REQUIRE(d.cvec != nullptr, "igemm: EMB_SILU needs cvec");
@@ -642,6 +751,20 @@ extern "C" void tdx_debug_set_igemm_trace(void* device_u64x128) {
   tdx::g_trace_ptr = reinterpret_cast<unsigned long long*>(device_u64x128);
 }
 extern "C" void tdx_debug_set_igemm_flags(int flags) { tdx::g_dbg_flags = flags; }
+
+extern "C" int tdx_igemm_choose_n(int32_t c_out, int32_t n_img, int32_t height, int32_t width,
+                                  const int32_t* a_channels, const int32_t* a_taps, int32_t n_seg) {
+  if (c_out < 64 || c_out % 64 || n_seg < 1 || n_seg > 3) return 64;
+  int stages = 0, chunks = 0;
+  for (int s = 0; s < n_seg; ++s) {
+    stages += (a_channels[s] / 64) * a_taps[s];
+    chunks += a_channels[s] / 64;
+  }
+  const int tiles = ((width + tdx::kTileW - 1) / tdx::kTileW) * ((height + tdx::kTileH - 1) / tdx::kTileH) * n_img;
+  int n = 64, res = 0, sb = 0;
+  tdx::choose_item_shape(c_out, tiles, stages, chunks, 0, &n, &res, &sb);
+  return n;
+}
 
 extern "C" int64_t tdx_igemm_packed_weight_elems(const int32_t* a_channels, const int32_t* a_taps, int32_t n_seg,
                                                  int32_t c_out) {

@@ -134,6 +134,8 @@ class FoldedWeights:
 
         g: dict = {}
         self.g = g
+        self.segs: dict = {}
+        self._packed: dict = {}
         if self.noise_dims > 0:
             g["noise_linear"] = effective_weight(sd["noise_linear.weight"]).t().contiguous()  # [in][out]
             if self.pos_emb:
@@ -158,25 +160,33 @@ class FoldedWeights:
                 w0 = effective_weight(sd[p + "conv_res0.weight"])
                 w1 = effective_weight(sd[p + "conv_res1.weight"]) * self.w_res
                 ws = effective_weight(sd[p + "conv_skip.weight"]) if (p + "conv_skip.weight") in sd else None
+                # effective GEMM operands as bf16 segment lists; packed per launch shape by packed()
+                seg = self.segs
                 if b["mode"] == "enc":
                     if ws is not None:
-                        g[p + "k1"] = pack_weight_segments([ws])
-                    g[p + "res0"] = pack_weight_segments([w0])
-                    g[p + "res1"] = pack_weight_segments([w1])
+                        seg[p + "k1"] = [ws.bfloat16()]
+                    seg[p + "res0"] = [w0.bfloat16()]
+                    seg[p + "res1"] = [w1.bfloat16()]
                 else:
                     if b.get("concat"):
                         cs = b["skip_channels"]
                         cx = b["cin"] - cs
                         s1, s2 = mp_concat_scales(cx, cs, self.cb)
-                        g[p + "res0"] = pack_weight_segments([w0[:, :cx].contiguous(), w0[:, cx:].contiguous()])
+                        seg[p + "res0"] = [w0[:, :cx].contiguous().bfloat16(), w0[:, cx:].contiguous().bfloat16()]
                         assert ws is not None
-                        g[p + "res1"] = pack_weight_segments([
-                            w1, (ws[:, :cx] * (s1 * self.w_skip)).contiguous(),
-                            (ws[:, cx:] * (s2 * self.w_skip)).contiguous()])
+                        seg[p + "res1"] = [w1.bfloat16(), (ws[:, :cx] * (s1 * self.w_skip)).contiguous().bfloat16(),
+                                           (ws[:, cx:] * (s2 * self.w_skip)).contiguous().bfloat16()]
                     else:
                         assert ws is None, "decoder block without concat but with a skip conv is not planned"
-                        g[p + "res0"] = pack_weight_segments([w0])
-                        g[p + "res1"] = pack_weight_segments([w1])
+                        seg[p + "res0"] = [w0.bfloat16()]
+                        seg[p + "res1"] = [w1.bfloat16()]
+
+    def packed(self, key: str, n_per_item: int) -> torch.Tensor:
+        """bf16 B operand of GEMM `key` packed for work items of `n_per_item` output channels (cached)."""
+        ck = (key, n_per_item)
+        if ck not in self._packed:
+            self._packed[ck] = pack_weight_segments([w.float() for w in self.segs[key]], n_per_item)
+        return self._packed[ck]
 
 
 class UNetProgram:
@@ -282,14 +292,16 @@ class UNetEmitter:
             slot += 1
         return res
 
-    def _igemm(self, prog, segs, packed, cout, h, w):
+    def _igemm(self, prog, segs, wkey, cout, h, w):
         d = L.TdxIgemmDesc()
         for i, (tensor, ch, taps) in enumerate(segs):
             d.a_ptr[i] = tensor.data_ptr()
             d.a_channels[i] = ch
             d.a_taps[i] = taps
         d.n_seg = len(segs)
-        d.b_packed = packed.data_ptr()
+        n_item = L.igemm_choose_n(cout, self.n, h, w, [(ch, taps) for _, ch, taps in segs])
+        d.n_per_item = n_item
+        d.b_packed = self.fw.packed(wkey, n_item).data_ptr()
         d.c_out = cout
         d.n_img, d.height, d.width = self.n, h, w
         return d
@@ -377,8 +389,8 @@ class UNetEmitter:
                 if b["resample"] == "down":
                     h, w = h // 2, w // 2
                     resid_sp = L.SP_DOWN2
-                if (key + "k1") in g:
-                    d = self._igemm(prog, [(cur["raw"], b["cin"], 1)], g[key + "k1"], cout, h, w)
+                if (key + "k1") in fw.segs:
+                    d = self._igemm(prog, [(cur["raw"], b["cin"], 1)], key + "k1", cout, h, w)
                     d.epi_flags = L.EPI_PNORM
                     xn = self.act(key + "xn", cout, h, w)
                     a_in = self.act(key + "a0", cout, h, w)
@@ -389,12 +401,12 @@ class UNetEmitter:
                 else:
                     a_in, resid, resid_pn = cur["act"], cur["raw"], 1
                 hbuf = self.act(key + "h", cout, h, w)
-                d = self._igemm(prog, [(a_in, cout, 9)], g[key + "res0"], cout, h, w)
+                d = self._igemm(prog, [(a_in, cout, 9)], key + "res0", cout, h, w)
                 d.epi_flags = L.EPI_EMB_SILU
                 d.cvec = self._cvec_ptr(key, cout, cvec_set)
                 self._set_out(d, 0, hbuf, L.OUT_RAW)
                 self._add_igemm(prog, d)
-                d = self._igemm(prog, [(hbuf, cout, 9)], g[key + "res1"], cout, h, w)
+                d = self._igemm(prog, [(hbuf, cout, 9)], key + "res1", cout, h, w)
                 d.epi_flags = L.EPI_RESID
                 d.resid = resid.data_ptr()
                 d.resid_spatial = resid_sp
@@ -416,16 +428,16 @@ class UNetEmitter:
                     segs0 = [(cur["act"], cx, 9), (sk["skip_act"], cs, 9)]
                 else:
                     segs0 = [(cur["act"], b["cin"], 9)]
-                d = self._igemm(prog, segs0, g[key + "res0"], cout, h, w)
+                d = self._igemm(prog, segs0, key + "res0", cout, h, w)
                 d.epi_flags = L.EPI_EMB_SILU
                 d.cvec = self._cvec_ptr(key, cout, cvec_set)
                 self._set_out(d, 0, hbuf, L.OUT_RAW)
                 self._add_igemm(prog, d)
                 if b.get("concat"):
-                    d = self._igemm(prog, [(hbuf, cout, 9), (cur["raw"], cx, 1), (sk["raw"], cs, 1)], g[key + "res1"],
+                    d = self._igemm(prog, [(hbuf, cout, 9), (cur["raw"], cx, 1), (sk["raw"], cs, 1)], key + "res1",
                                     cout, h, w)
                 else:
-                    d = self._igemm(prog, [(hbuf, cout, 9)], g[key + "res1"], cout, h, w)
+                    d = self._igemm(prog, [(hbuf, cout, 9)], key + "res1", cout, h, w)
                     d.epi_flags = L.EPI_RESID
                     d.resid = cur["raw"].data_ptr()
                     d.resid_spatial = resid_sp

@@ -38,6 +38,7 @@ class Case:
     clip: float = 0.0
     outs: list = field(default_factory=lambda: [(L.OUT_RAW, L.SP_SAME, 1.0)])
     wscale: float = 1.0
+    n_item: int = 0   # 0 = let the library choose (tdx_igemm_choose_n)
     seed: int = 0
 
 
@@ -102,7 +103,8 @@ def reference(case: Case, acts, wts, cvec, resid):
 def run_cuda(case: Case, acts, wts, cvec, resid):
     dev = acts[0].device
     a_dev = [to_nc8hw8(a) for a in acts]
-    b = pack_weight_segments(wts).to(dev)
+    n_item = case.n_item or L.igemm_choose_n(case.cout, case.n, case.h, case.w, case.segs)
+    b = pack_weight_segments(wts, n_item).to(dev)
     r_dev = to_nc8hw8(resid)
     d = L.TdxIgemmDesc()
     for i, (c, t) in enumerate(case.segs):
@@ -112,6 +114,7 @@ def run_cuda(case: Case, acts, wts, cvec, resid):
     d.n_seg = len(case.segs)
     d.b_packed = b.data_ptr()
     d.c_out = case.cout
+    d.n_per_item = n_item
     d.n_img, d.height, d.width = case.n, case.h, case.w
     d.epi_flags = case.epi
     d.cvec = cvec.contiguous().data_ptr()
@@ -170,6 +173,13 @@ def default_cases() -> list[Case]:
              outs=[(L.OUT_RAW, L.SP_SAME, 1.0), (L.OUT_PNORM_SILU, L.SP_DOWN2, 1.0)]),
         Case("cluster4_k1_pnorm", [(192, 1)], 256, 1, 32, 32, epi=P,
              outs=[(L.OUT_RAW, L.SP_SAME, 1.0), (L.OUT_SILU, L.SP_SAME, 1.0)]),
+        Case("n128_forced_resid_pnorm", [(128, 9)], 256, 1, 32, 32, epi=R, resid_pnorm=1, n_item=128,
+             outs=[(L.OUT_RAW, L.SP_SAME, 1.0), (L.OUT_PNORM_SILU, L.SP_SAME, 1.0)]),
+        Case("n256_forced_emb", [(64, 9)], 256, 1, 32, 32, epi=E, n_item=256),
+        Case("n192_forced_pnorm_2pass", [(64, 9)], 192, 1, 32, 32, epi=R, resid_pnorm=1, n_item=192,
+             outs=[(L.OUT_RAW, L.SP_SAME, 1.0), (L.OUT_PNORM_SILU, L.SP_DOWN2, 1.0), (L.OUT_SILU, L.SP_SAME, 0.9)]),
+        Case("n64_forced_c256", [(256, 9)], 256, 1, 32, 32, epi=R, n_item=64),
+        Case("resident_multi_item_per_cta", [(64, 9)], 64, 3, 128, 128, epi=E),
         Case("clip_active", [(64, 9)], 64, 1, 16, 16, epi=R, clip=0.5),
         Case("clip_no_resid", [(64, 9), (64, 1)], 64, 1, 16, 16, clip=0.3),
     ]

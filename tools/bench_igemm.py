@@ -47,12 +47,13 @@ def main():
         n = args.batch
         acts = [to_nc8hw8(torch.randn(n, c, res, res, device=dev)) for c, _ in segs]
         wts = [torch.randn(cout, c, 3 if t == 9 else 1, 3 if t == 9 else 1, device=dev) * 0.02 for c, t in segs]
-        b = pack_weight_segments(wts)
+        n_item = L.igemm_choose_n(cout, n, res, res, segs)
+        b = pack_weight_segments(wts, n_item)
         out = torch.empty(n, cout // 8, res, res, 8, dtype=torch.bfloat16, device=dev)
         d = L.TdxIgemmDesc()
         for i, (c, t) in enumerate(segs):
             d.a_ptr[i] = acts[i].data_ptr(); d.a_channels[i] = c; d.a_taps[i] = t
-        d.n_seg = len(segs); d.b_packed = b.data_ptr(); d.c_out = cout
+        d.n_seg = len(segs); d.b_packed = b.data_ptr(); d.c_out = cout; d.n_per_item = n_item
         d.n_img, d.height, d.width = n, res, res
         d.out[0].ptr = out.data_ptr(); d.out[0].kind = L.OUT_RAW; d.out[0].scale = 1.0
         stream = L.current_stream_ptr()

@@ -58,7 +58,7 @@ def tap_probe(dev):
             b = pack_weight_segments([w]).to(dev)
             o = torch.full((1, 8, 16, 8, 8), float("nan"), dtype=torch.bfloat16, device=dev)
             d.a_ptr[0] = an.data_ptr(); d.a_channels[0] = 64; d.a_taps[0] = 9; d.n_seg = 1
-            d.b_packed = b.data_ptr(); d.c_out = 64; d.n_img = 1; d.height = 16; d.width = 8
+            d.b_packed = b.data_ptr(); d.c_out = 64; d.n_per_item = 64; d.n_img = 1; d.height = 16; d.width = 8
             d.out[0].ptr = o.data_ptr(); d.out[0].kind = L.OUT_RAW; d.out[0].spatial = L.SP_SAME; d.out[0].scale = 1.0
             L.check(L.lib().tdx_igemm_run(C.byref(d), L.current_stream_ptr()))
             torch.cuda.synchronize()

@@ -9,7 +9,7 @@ import torch
 from terrain_diffusion_b200 import _lib as L
 from terrain_diffusion_b200.layout import pack_weight_segments, to_nc8hw8
 
-SHAPES = [("64->64 @256", [(64, 9)], 64, 256), ("128->128 @128", [(128, 9)], 128, 128),
+SHAPES = [("64->64 @128 (<=2 items/CTA)", [(64, 9)], 64, 128), ("64->64 @256", [(64, 9)], 64, 256), ("128->128 @128", [(128, 9)], 128, 128),
           ("256->256 @32", [(256, 9)], 256, 32), ("192->192 @64", [(192, 9)], 192, 64)]
 NAMES = ["A-prod start", "mma: tmem free", "mma: A landed", "mma: issued+commit", "epi: waiting", "epi: acc ready",
          "epi: done"]
@@ -26,13 +26,14 @@ def main():
     for name, segs, cout, res in SHAPES:
         acts = [to_nc8hw8(torch.randn(1, c, res, res, device=dev)) for c, _ in segs]
         wts = [torch.randn(cout, c, 3, 3, device=dev) * 0.02 for c, t in segs]
-        b = pack_weight_segments(wts)
+        n_item = L.igemm_choose_n(cout, 1, res, res, segs)
+        b = pack_weight_segments(wts, n_item)
         out = torch.empty(1, cout // 8, res, res, 8, dtype=torch.bfloat16, device=dev)
         cvec = torch.ones(1, cout, device=dev)
         d = L.TdxIgemmDesc()
         for i, (c, t) in enumerate(segs):
             d.a_ptr[i] = acts[i].data_ptr(); d.a_channels[i] = c; d.a_taps[i] = t
-        d.n_seg = len(segs); d.b_packed = b.data_ptr(); d.c_out = cout
+        d.n_seg = len(segs); d.b_packed = b.data_ptr(); d.c_out = cout; d.n_per_item = n_item
         d.n_img, d.height, d.width = 1, res, res
         d.epi_flags = L.EPI_EMB_SILU; d.cvec = cvec.data_ptr()
         d.out[0].ptr = out.data_ptr(); d.out[0].kind = L.OUT_RAW; d.out[0].scale = 1.0
