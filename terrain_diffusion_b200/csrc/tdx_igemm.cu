@@ -58,6 +58,10 @@ struct IgemmParams {
   int SB;                     // B ring depth
   int b_stage_bytes;          // ncta * 128
   int resident;               // the whole weight set of an item fits the ring: loaded once per CTA, reused by every item
+  int ksplit;                 // split-K: the K loop (64-channel chunks) of a work item is shared by ksplit CTAs
+  int chunks_total;           // sum of seg_chunks
+  float* ws;                  // split-K fp32 partial accumulators [group][ksplit-1][ncta][128]
+  int* ws_count;              // split-K arrival counters [group]
   int H, W, nimg, tiles_x, tiles_y, num_items;
   int stages_per_item;
   int epi;
@@ -71,14 +75,38 @@ struct IgemmParams {
   unsigned long long* trace;  // debug: per-item phase timestamps of CTA 0 (tools/trace_igemm.py), normally null
 };
 
+// Flat 64-channel chunk index f (over all segments) -> (segment, chunk in segment); [f0, f1) = this CTA's K range.
+__device__ __forceinline__ void chunk_range(const IgemmParams& p, int item, int& f0, int& f1) {
+  const int k = item % p.ksplit;
+  f0 = (p.chunks_total * k) / p.ksplit;
+  f1 = (p.chunks_total * (k + 1)) / p.ksplit;
+}
+__device__ __forceinline__ void chunk_seg(const IgemmParams& p, int f, int& seg, int& ch) {
+  seg = 0;
+  ch = f;
+  if (ch >= p.seg_chunks[0]) { ch -= p.seg_chunks[0]; seg = 1; }
+  if (seg == 1 && ch >= p.seg_chunks[1]) { ch -= p.seg_chunks[1]; seg = 2; }
+}
+__device__ __forceinline__ int stages_before(const IgemmParams& p, int f) {
+  int n = 0, rem = f;
+  for (int s = 0; s < p.nseg && rem > 0; ++s) {
+    const int c = rem < p.seg_chunks[s] ? rem : p.seg_chunks[s];
+    n += c * p.seg_taps[s];
+    rem -= c;
+  }
+  return n;
+}
+
 #define TDX_TRACE(slot, it)                                                                  \
   do {                                                                                       \
     if (p.trace && blockIdx.x == 0 && (it) < 16) p.trace[(it) * 8 + (slot)] = clock64();     \
   } while (0)
 
+// item = ((tile * nsplit) + split) * ksplit + kpart
 __device__ __forceinline__ void decode_item(const IgemmParams& p, int item, int& split, int& img, int& Y0, int& X0) {
-  split = item % p.nsplit;
-  int tile = item / p.nsplit;
+  const int rest = item / p.ksplit;
+  split = rest % p.nsplit;
+  int tile = rest / p.nsplit;
   int tx = tile % p.tiles_x;
   int t = tile / p.tiles_x;
   int ty = t % p.tiles_y;
@@ -149,6 +177,12 @@ __device__ __forceinline__ void store_group(const OutCtx& o, int group, const fl
   }
 }
 
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
 __device__ __forceinline__ void load_acc32(uint32_t taddr, float (&v)[32]) {
   uint32_t r[32];
   tmem_ld32(taddr, r);
@@ -178,6 +212,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CU
 
   const int warp = threadIdx.x >> 5;   // warp-uniform role id
   const int lane = threadIdx.x & 31;
+  if (p.trace && blockIdx.x == 0 && threadIdx.x == 0) p.trace[126] = clock64();
 
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&tm0);
@@ -223,17 +258,19 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CU
       int split, img, Y0, X0;
       decode_item(p, item, split, img, Y0, X0);
       if (lane == 0) TDX_TRACE(0, it);
-      for (int seg = 0; seg < p.nseg; ++seg) {
+      int f0, f1;
+      chunk_range(p, item, f0, f1);
+      for (int f = f0; f < f1; ++f) {
+        int seg, ch;
+        chunk_seg(p, f, seg, ch);
         const CUtensorMap* tm = seg == 0 ? &tm0 : (seg == 1 ? &tm1 : &tm2);
-        for (int ch = 0; ch < p.seg_chunks[seg]; ++ch) {
-          mbar_wait(&a_empty[sa], ph ^ 1, 100 + sa);
-          if (elect_one()) {
-            mbar_expect_tx(&a_full[sa], kAStageBytes);
-            tma_load_4d(tm, &a_full[sa], a_ring + sa * kAStageBytes, (X0 - 1) * 8, Y0 - 1, ch * 8, img);
-          }
-          __syncwarp();
-          if (++sa == kSA) { sa = 0; ph ^= 1; }
+        mbar_wait(&a_empty[sa], ph ^ 1, 100 + sa);
+        if (elect_one()) {
+          mbar_expect_tx(&a_full[sa], kAStageBytes);
+          tma_load_4d(tm, &a_full[sa], a_ring + sa * kAStageBytes, (X0 - 1) * 8, Y0 - 1, ch * 8, img);
         }
+        __syncwarp();
+        if (++sa == kSA) { sa = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
@@ -242,9 +279,13 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CU
     int sb = 0;
     uint32_t ph = 0;
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
-      const int split = item % p.nsplit;   // constant per CTA: gridDim.x is a multiple of nsplit
-      const uint8_t* bsrc = reinterpret_cast<const uint8_t*>(p.B) + (size_t)split * p.stages_per_item * p.b_stage_bytes;
-      for (int ks = 0; ks < p.stages_per_item; ++ks) {
+      const int split = (item / p.ksplit) % p.nsplit;   // constant per CTA: gridDim.x is a multiple of nsplit*ksplit
+      int f0, f1;
+      chunk_range(p, item, f0, f1);
+      const int st0 = stages_before(p, f0), st1 = stages_before(p, f1);
+      const uint8_t* bsrc = reinterpret_cast<const uint8_t*>(p.B) +
+                            ((size_t)split * p.stages_per_item + st0) * p.b_stage_bytes;
+      for (int ks = 0; ks < st1 - st0; ++ks) {
         if (!p.resident) mbar_wait(&b_empty[sb], ph ^ 1, 200 + sb);
         if (elect_one()) {
           if (p.dbg & 2) {
@@ -286,12 +327,16 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CU
       const uint32_t d_tmem = tmem_base + acc * kAccCols;
       const bool steady = p.resident && it > 0;   // weights already in the ring: no per-stage handshakes
       uint32_t accumulate = 0;
-      for (int seg = 0; seg < p.nseg; ++seg) {
-        const int taps = p.seg_taps[seg];
-        for (int ch = 0; ch < p.seg_chunks[seg]; ++ch) {
+      int f0, f1;
+      chunk_range(p, item, f0, f1);
+      {
+        for (int f = f0; f < f1; ++f) {
+          int seg, ch;
+          chunk_seg(p, f, seg, ch);
+          const int taps = p.seg_taps[seg];
           mbar_wait(&a_full[sa], pha, 400 + sa);
           tc_fence_after();
-          if (lane == 0 && seg == 0 && ch == 0) TDX_TRACE(2, it);
+          if (lane == 0 && f == f0) TDX_TRACE(2, it);
           const uint32_t a16 = a_ring16 + sa * (kAStageBytes >> 4);
           if (steady && taps == 9) {
             // ---- 36 MMAs back to back
@@ -370,6 +415,52 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CU
       const uint32_t taddr = tmem_base + acc * kAccCols + ((uint32_t)(q * 32) << 16);
       const float* cvb = p.cvec ? p.cvec + (size_t)img * p.cout + chbase : nullptr;
 
+      // ---------------- split-K: ksplit CTAs each hold a partial sum of the same output tile.  Parts 1.. publish their
+      // fp32 accumulator through an L2-resident workspace; part 0 adds them and runs the epilogue.  (Launches with
+      // ksplit > 1 have one item per CTA and at most one CTA per SM, so all parts are co-resident.)
+      const int kpart = item % p.ksplit, group = item / p.ksplit;
+      float* wsg = p.ws + (size_t)group * (p.ksplit - 1) * p.ncta * 128;
+      if (p.ksplit > 1 && kpart > 0) {
+        mbar_wait(&t_full[acc], accph, 600 + acc);
+        tc_fence_after();
+        float* dst = wsg + (size_t)(kpart - 1) * p.ncta * 128 + m;
+        for (int ck = half; ck < nchunks; ck += 2) {
+          float v[32];
+          __syncwarp();
+          load_acc32(taddr + ck * 32, v);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) __stcg(dst + (size_t)(ck * 32 + j) * 128, v[j]);
+        }
+        __threadfence();
+        named_bar_sync(9, 32 * kEpiWarps);
+        if (warp == 4 && lane == 0) atomicAdd(p.ws_count + group, 1);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&t_empty[acc]);
+        continue;
+      }
+      if (p.ksplit > 1) {
+        if (warp == 4 && lane == 0) {
+          long long t0 = clock64();
+          while (ld_acquire_gpu(p.ws_count + group) < p.ksplit - 1) {
+            if (clock64() - t0 > TDX_WAIT_LIMIT) {
+              printf("tdx: split-K partials wait timeout block=%d\n", (int)blockIdx.x);
+              __trap();
+            }
+          }
+          p.ws_count[group] = 0;   // ready for the next launch
+        }
+        named_bar_sync(9, 32 * kEpiWarps);
+      }
+      // adds the other parts' partial sums to accumulator chunk ck (no-op without split-K)
+      auto add_partials = [&](int ck, float (&v)[32]) {
+        for (int kp = 0; kp < p.ksplit - 1; ++kp) {
+          const float* src = wsg + (size_t)kp * p.ncta * 128 + (size_t)(ck * 32) * 128 + m;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += __ldcg(src + (size_t)j * 128);
+        }
+      };
+
       if (fast_res0) {
         // ---------------- res0: v = mp_silu(acc * c) -> one bf16 output (the common case: half of all launches)
         const size_t oplane = (size_t)p.H * p.W;
@@ -386,6 +477,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CU
           float v[32];
           __syncwarp();
           load_acc32(taddr + ck * 32, v);
+          add_partials(ck, v);
           if (valid) {
             uint4* optr = obase + (size_t)(ck * 4) * oplane;
 #pragma unroll
@@ -465,6 +557,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CU
         auto compute_v = [&](int ck, float (&v)[32]) {
           __syncwarp();
           load_acc32(taddr + ck * 32, v);
+          add_partials(ck, v);
           if (p.epi & TDX_EPI_EMB_SILU) {
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
@@ -593,11 +686,14 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CU
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
+  if (p.trace && blockIdx.x == 0 && threadIdx.x == 96) p.trace[125] = clock64();
 }
 
 // ---------------------------------------------------------------------------------------------------- host side
 static unsigned long long* g_trace_ptr = nullptr;
 static int g_dbg_flags = 0;
+
+static int ensure_scratch(float** ws, int** cnt);
 
 int igemm_prepare() {
   static bool attr_set = false;
@@ -605,7 +701,9 @@ int igemm_prepare() {
     TDX_CHECK_CUDA(cudaFuncSetAttribute(igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
     attr_set = true;
   }
-  return TDX_OK;
+  float* ws;
+  int* cnt;
+  return ensure_scratch(&ws, &cnt);
 }
 
 static bool needs_norm(const TdxIgemmDesc& d) {
@@ -615,41 +713,78 @@ static bool needs_norm(const TdxIgemmDesc& d) {
   return false;
 }
 
-// Choose the output-channel width of a work item (MMA N).  Model (cycles), from measurements on B200:
-//   * an SS-mode M=128 K=16 tcgen05.mma costs max(86, N/2) cycles (tools/probe/mma_probe.cu);
+// Split-K scratch (fp32 partial accumulators + arrival counters), one per device, allocated outside stream capture.
+constexpr size_t kWsBytes = 20u << 20;
+constexpr int kWsCounters = 256;
+static float* g_ws[16] = {nullptr};
+static int* g_ws_count[16] = {nullptr};
+
+static int ensure_scratch(float** ws, int** cnt) {
+  int dev = 0;
+  TDX_CHECK_CUDA(cudaGetDevice(&dev));
+  TDX_REQUIRE(dev >= 0 && dev < 16, "igemm: device index %d out of range", dev);
+  if (!g_ws[dev]) {
+    TDX_CHECK_CUDA(cudaMalloc(&g_ws[dev], kWsBytes));
+    TDX_CHECK_CUDA(cudaMalloc(&g_ws_count[dev], kWsCounters * sizeof(int)));
+    TDX_CHECK_CUDA(cudaMemset(g_ws_count[dev], 0, kWsCounters * sizeof(int)));
+  }
+  *ws = g_ws[dev];
+  *cnt = g_ws_count[dev];
+  return TDX_OK;
+}
+
+// Choose the output-channel width of a work item (MMA N) and the split-K factor.  Model (cycles), from measurements
+// on B200:
+//   * an SS-mode M=128 K=16 tcgen05.mma costs max(86, N/2) cycles when issued stage by stage (~70 back to back from
+//     smem-resident weights) -- tools/probe/mma_probe.cu, tools/trace_igemm.py;
 //   * L2 -> SM delivers ~2.8 KB/clk chip-wide; per item the A patches (23 KB per 64 input channels) and, unless the
-//     item's whole weight slice fits the B ring ("resident": loaded once per CTA), the weights (N*128 B per stage).
-static void choose_item_shape(int cout, int tiles, int stages, int chunks, int forced, int* ncta_out,
-                              int* resident_out, int* sb_out) {
-  if (!forced && getenv("TDX_IGEMM_N")) forced = atoi(getenv("TDX_IGEMM_N"));
-  if (forced && (forced > cout || cout % forced)) forced = 0;
+//     item's whole weight slice fits the B ring ("resident": loaded once per CTA), the weights (N*128 B per stage);
+//   * layers with fewer work items than SMs are a serial MMA chain per CTA: split their K loop over `ks` CTAs that
+//     reduce through an L2-resident fp32 workspace (only when every part fits on the chip at once).
+struct ItemShape { int ncta, resident, sb, ksplit; };
+
+static ItemShape choose_item_shape(int cout, int tiles, int stages, int chunks, int forced_n, bool allow_ksplit) {
+  if (!forced_n && getenv("TDX_IGEMM_N")) forced_n = atoi(getenv("TDX_IGEMM_N"));
+  if (forced_n && (forced_n > cout || cout % forced_n)) forced_n = 0;
+  int forced_k = getenv("TDX_IGEMM_KSPLIT") ? atoi(getenv("TDX_IGEMM_KSPLIT")) : 0;
   const int ring_budget = kSmemBudget - kSA * kAStageBytes - kSmemMisc;
   double best = 1e30;
-  int best_n = 64, best_res = 0, best_sb = 2;
+  ItemShape bs = {64, 0, 2, 1};
   for (int n = 64; n <= 256 && n <= cout; n += 64) {
     if (cout % n) continue;
-    if (forced && n != forced) continue;
+    if (forced_n && n != forced_n) continue;
     const int stage_bytes = n * 128;
-    const int resident = (stages * stage_bytes <= ring_budget && stages <= kMaxSB) ? 1 : 0;
-    int sb = resident ? stages : ring_budget / stage_bytes;
-    if (sb > kMaxSB) sb = kMaxSB;
-    if (sb < 2) continue;
     const int nsplit = cout / n;
     const long items = (long)tiles * nsplit;
-    int grid = items < sm_count() ? (int)items : sm_count();
-    grid -= grid % nsplit;
-    const double rounds = (double)((items + grid - 1) / grid);
-    const double mma = rounds * stages * 4.0 * (n / 2.0 > 86.0 ? n / 2.0 : 86.0);
-    const double a_bytes = (double)items * chunks * kAStageBytes;
-    const double b_bytes = resident ? (double)grid * stages * stage_bytes : (double)items * stages * stage_bytes;
-    const double l2 = (a_bytes + b_bytes) / 2800.0;
-    const double epi = rounds * (n / 32) * 150.0 / 2.0;
-    const double t = (mma > l2 ? mma : l2) + epi + 4000.0;
-    if (t < best) { best = t; best_n = n; best_res = resident; best_sb = sb; }
+    for (int ks = 1; ks <= 8; ++ks) {
+      if (ks > 1 && (!allow_ksplit || ks > chunks || items * ks > sm_count())) break;
+      if (forced_k && allow_ksplit && ks != forced_k && forced_k <= chunks && items * forced_k <= sm_count()) continue;
+      const int my_stages = (stages + ks - 1) / ks;
+      const int resident = (ks == 1 && stages * stage_bytes <= ring_budget && stages <= kMaxSB) ? 1 : 0;
+      int sb = resident ? stages : ring_budget / stage_bytes;
+      if (sb > kMaxSB) sb = kMaxSB;
+      if (sb < 2) continue;
+      if (ks > 1 && ((size_t)items * (ks - 1) * n * 512 > kWsBytes || items > kWsCounters)) continue;
+      int grid = items * ks < sm_count() ? (int)(items * ks) : sm_count();
+      grid -= grid % (nsplit * ks);
+      if (grid <= 0) continue;
+      const double rounds = (double)((items * ks + grid - 1) / grid);
+      const double cyc = n / 2.0 > 86.0 ? n / 2.0 : 86.0;
+      const double mma = rounds * my_stages * 4.0 * cyc + 800.0;
+      const double a_bytes = (double)items * chunks * kAStageBytes;
+      const double b_bytes = resident ? (double)grid * stages * stage_bytes : (double)items * stages * stage_bytes;
+      const double l2 = (a_bytes + b_bytes) / 2800.0;
+      const double per_sm = ((double)(chunks * kAStageBytes + stages * stage_bytes) / ks) / 56.0;  // one SM's L2 port
+      const double epi = rounds * (n / 32) * 150.0 / 2.0;
+      const double red = ks > 1 ? (ks - 1) * n * 512.0 / 56.0 + 1500.0 : 0.0;
+      double t = mma;
+      if (l2 > t) t = l2;
+      if (per_sm > t) t = per_sm;
+      t += epi + red;
+      if (t < best) { best = t; bs = {n, resident, sb, ks}; }
+    }
   }
-  *ncta_out = best_n;
-  *resident_out = best_res;
-  *sb_out = best_sb;
+  return bs;
 }
 
 int igemm_launch(const TdxIgemmDesc& d, const CUtensorMap* tms, cudaStream_t stream) {
@@ -672,10 +807,21 @@ int igemm_launch(const TdxIgemmDesc& d, const CUtensorMap* tms, cudaStream_t str
   p.tiles_x = (d.width + kTileW - 1) / kTileW;
   p.tiles_y = (d.height + kTileH - 1) / kTileH;
   const int tiles = p.tiles_x * p.tiles_y * d.n_img;
-  choose_item_shape(d.c_out, tiles, p.stages_per_item, chunks, d.n_per_item, &p.ncta, &p.resident, &p.SB);
+  const bool norm_split = needs_norm(d);
+  ItemShape shp = choose_item_shape(d.c_out, tiles, p.stages_per_item, chunks, d.n_per_item, !norm_split);
+  if (norm_split && d.c_out / shp.ncta == 1) shp = choose_item_shape(d.c_out, tiles, p.stages_per_item, chunks, shp.ncta, true);
+  p.ncta = shp.ncta;
+  p.resident = shp.resident;
+  p.SB = shp.sb;
+  p.ksplit = shp.ksplit;
+  p.chunks_total = chunks;
   p.nsplit = d.c_out / p.ncta;
   p.b_stage_bytes = p.ncta * 128;
-  p.num_items = tiles * p.nsplit;
+  p.num_items = tiles * p.nsplit * p.ksplit;
+  if (p.ksplit > 1) {
+    int rc_ws = ensure_scratch(&p.ws, &p.ws_count);
+    if (rc_ws != TDX_OK) return rc_ws;
+  }
   p.epi = d.epi_flags;
   p.cluster_stats = (needs_norm(d) && p.nsplit > 1) ? 1 : 0;
   p.cvec = d.cvec;
@@ -692,7 +838,7 @@ int igemm_launch(const TdxIgemmDesc& d, const CUtensorMap* tms, cudaStream_t str
   if (rc_prep != TDX_OK) return rc_prep;
   // grid: one CTA per SM at most, a multiple of nsplit so the slices of an M tile always run side by side
   int grid = p.num_items < sm_count() ? p.num_items : sm_count();
-  grid -= grid % p.nsplit;
+  grid -= grid % (p.nsplit * p.ksplit);
   const int smem = kSA * kAStageBytes + p.SB * p.b_stage_bytes + kSmemMisc;
   const CUtensorMap& t0 = tms[0];
   const CUtensorMap& t1 = tms[d.n_seg > 1 ? 1 : 0];
@@ -761,9 +907,22 @@ extern "C" int tdx_igemm_choose_n(int32_t c_out, int32_t n_img, int32_t height, 
     chunks += a_channels[s] / 64;
   }
   const int tiles = ((width + tdx::kTileW - 1) / tdx::kTileW) * ((height + tdx::kTileH - 1) / tdx::kTileH) * n_img;
-  int n = 64, res = 0, sb = 0;
-  tdx::choose_item_shape(c_out, tiles, stages, chunks, 0, &n, &res, &sb);
-  return n;
+  return tdx::choose_item_shape(c_out, tiles, stages, chunks, 0, true).ncta;
+}
+
+// Debug: the (n_per_item, ksplit, resident, ring depth) the launch heuristics pick for a shape.
+extern "C" void tdx_debug_igemm_plan(int32_t c_out, int32_t n_img, int32_t height, int32_t width,
+                                     const int32_t* a_channels, const int32_t* a_taps, int32_t n_seg,
+                                     int32_t n_per_item, int32_t needs_norm, int32_t* out4) {
+  int stages = 0, chunks = 0;
+  for (int s = 0; s < n_seg; ++s) {
+    stages += (a_channels[s] / 64) * a_taps[s];
+    chunks += a_channels[s] / 64;
+  }
+  const int tiles = ((width + tdx::kTileW - 1) / tdx::kTileW) * ((height + tdx::kTileH - 1) / tdx::kTileH) * n_img;
+  tdx::ItemShape shp = tdx::choose_item_shape(c_out, tiles, stages, chunks, n_per_item, !needs_norm);
+  if (needs_norm && c_out / shp.ncta == 1) shp = tdx::choose_item_shape(c_out, tiles, stages, chunks, shp.ncta, true);
+  out4[0] = shp.ncta; out4[1] = shp.ksplit; out4[2] = shp.resident; out4[3] = shp.sb;
 }
 
 extern "C" int64_t tdx_igemm_packed_weight_elems(const int32_t* a_channels, const int32_t* a_taps, int32_t n_seg,
