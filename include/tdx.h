@@ -30,7 +30,7 @@ extern "C" {
 const char* tdx_last_error(void);
 /* Library + device probe: fills sm count, compute capability; fails if the device is not sm_100. */
 int tdx_device_info(int* sm_count, int* cc_major, int* cc_minor);
-/* sizeof() of the public structs (0: TdxOutSpec, 1: TdxIgemmDesc, 2: TdxConvInDesc, 3: TdxConvOutDesc, 4: TdxEmbedBlock, 5: TdxEmbedDesc) so bindings can verify their layout. */
+/* sizeof() of the public structs (0: TdxOutSpec, 1: TdxIgemmDesc, 2: TdxConvInDesc, 3: TdxConvOutDesc, 4: TdxEmbedBlock, 5: TdxEmbedDesc, 6: TdxAttnDesc) so bindings can verify their layout. */
 int tdx_abi_sizeof(int which);
 
 /* ------------------------------------------------------------------------------------------------------------------
@@ -149,6 +149,20 @@ typedef struct TdxEmbedDesc {
 int tdx_embed_run(const TdxEmbedDesc* desc, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
+ * Cosine self-attention core of UNetBlock.attn (models/unet_block.py:102-108) between the qkv and proj 1x1 convs
+ * (which run as tdx_igemm launches): per-head pixel-norm of q, k, v; softmax(q^T k / sqrt(d)); weighted sum of v.
+ * q, k, v, out: bf16 NC8HW8 with channel = head*64 + d, spatial size tokens = H*W.
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct TdxAttnDesc {
+  const void* q;
+  const void* k;
+  const void* v;
+  void* out;
+  int32_t n_img, heads, head_dim, tokens;
+} TdxAttnDesc;
+int tdx_attn_run(const TdxAttnDesc* desc, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
  * Scheduler / consistency / blend elementwise kernels (fp32, vectorised).
  * ------------------------------------------------------------------------------------------------------------------ */
 /* scheduler.step closed form on a standalone model output (dpmsolver.py:650-726); coef = host floats. */
@@ -185,13 +199,14 @@ int tdx_program_add_conv_in(TdxProgram* p, const TdxConvInDesc* d);
 int tdx_program_add_igemm(TdxProgram* p, const TdxIgemmDesc* d);
 int tdx_program_add_conv_out(TdxProgram* p, const TdxConvOutDesc* d);
 int tdx_program_add_embed(TdxProgram* p, const TdxEmbedDesc* d);
+int tdx_program_add_attn(TdxProgram* p, const TdxAttnDesc* d);
 int tdx_program_num_launches(const TdxProgram* p);
 /* use_graph != 0: capture on first run, replay afterwards. */
 int tdx_program_run(TdxProgram* p, int use_graph, void* stream);
 /* Capture + instantiate + upload the graph without running it (keeps one-time costs out of timed regions). */
 int tdx_program_instantiate(TdxProgram* p, void* stream);
 /* Eager run with a CUDA event pair around every launch: ms_per_launch[i] = device time of launch i (in program
- * order, tdx_program_num_launches entries); kinds[i] = 0 conv_in, 1 igemm, 2 conv_out, 3 embed.  Synchronises. */
+ * order, tdx_program_num_launches entries); kinds[i] = 0 conv_in, 1 igemm, 2 conv_out, 3 embed, 4 attn.  Synchronises. */
 int tdx_program_profile(TdxProgram* p, float* ms_per_launch, int32_t* kinds, void* stream);
 int tdx_program_destroy(TdxProgram* p);
 

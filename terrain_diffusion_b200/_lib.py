@@ -55,7 +55,12 @@ class TdxEmbedDesc(C.Structure):
     ]
 
 
-ABI_STRUCTS = [TdxOutSpec, TdxIgemmDesc, TdxConvInDesc, TdxConvOutDesc, TdxEmbedBlock, TdxEmbedDesc]
+class TdxAttnDesc(C.Structure):
+    _fields_ = [("q", C.c_void_p), ("k", C.c_void_p), ("v", C.c_void_p), ("out", C.c_void_p), ("n_img", C.c_int32),
+                ("heads", C.c_int32), ("head_dim", C.c_int32), ("tokens", C.c_int32)]
+
+
+ABI_STRUCTS = [TdxOutSpec, TdxIgemmDesc, TdxConvInDesc, TdxConvOutDesc, TdxEmbedBlock, TdxEmbedDesc, TdxAttnDesc]
 
 OUT_NONE, OUT_RAW, OUT_SILU, OUT_PNORM_SILU = 0, 1, 2, 3
 SP_SAME, SP_DOWN2, SP_UP2 = 0, 1, 2
@@ -94,7 +99,7 @@ def _declare(l: C.CDLL) -> None:
         if l.tdx_abi_sizeof(i) != C.sizeof(st):
             raise TdxError(f"ABI mismatch for {st.__name__}: C {l.tdx_abi_sizeof(i)} vs ctypes {C.sizeof(st)}")
     for name, desc in (("tdx_conv_in_run", TdxConvInDesc), ("tdx_conv_out_run", TdxConvOutDesc),
-                       ("tdx_embed_run", TdxEmbedDesc)):
+                       ("tdx_embed_run", TdxEmbedDesc), ("tdx_attn_run", TdxAttnDesc)):
         fn = getattr(l, name)
         fn.restype = C.c_int
         fn.argtypes = [C.POINTER(desc), C.c_void_p]
@@ -119,7 +124,8 @@ def _declare(l: C.CDLL) -> None:
     l.tdx_program_create.restype = C.c_int
     l.tdx_program_create.argtypes = [C.POINTER(C.c_void_p)]
     for name, desc in (("tdx_program_add_conv_in", TdxConvInDesc), ("tdx_program_add_igemm", TdxIgemmDesc),
-                       ("tdx_program_add_conv_out", TdxConvOutDesc), ("tdx_program_add_embed", TdxEmbedDesc)):
+                       ("tdx_program_add_conv_out", TdxConvOutDesc), ("tdx_program_add_embed", TdxEmbedDesc),
+                       ("tdx_program_add_attn", TdxAttnDesc)):
         fn = getattr(l, name)
         fn.restype = C.c_int
         fn.argtypes = [C.c_void_p, C.POINTER(desc)]

@@ -119,6 +119,7 @@ extern "C" int tdx_abi_sizeof(int which) {
     case 3: return (int)sizeof(TdxConvOutDesc);
     case 4: return (int)sizeof(TdxEmbedBlock);
     case 5: return (int)sizeof(TdxEmbedDesc);
+    case 6: return (int)sizeof(TdxAttnDesc);
     default: return -1;
   }
 }

@@ -397,33 +397,39 @@ __global__ void __launch_bounds__(256) embed_kernel(const __grid_constant__ Embe
     }
   }
   __syncthreads();
-  // c[n] = sum_j W^T[j][n] * emb[j] + 1: the 256 threads cover (n, quarter-of-j) so all of them stream weights
+  // c[n] = sum_j W^T[j][n] * emb[j] + 1: the 256 threads cover (n, part-of-j) so all of them stream weights
   const TdxEmbedBlock& blk = p.blocks[b];
   __shared__ float part[4][256];
+  __shared__ float cfull[1024];
   const int parts = blk.c_out <= 64 ? 4 : (blk.c_out <= 128 ? 2 : 1);
-  const int n = threadIdx.x % (256 / parts), part_id = threadIdx.x / (256 / parts);
-  const int jlen = p.E / parts, j0 = part_id * jlen;
-  float acc = 0.f;
-  if (n < blk.c_out) {
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  const int per = 256 / parts;
+  float sq = 0.f;
+  for (int n0 = 0; n0 < blk.c_out; n0 += per) {
+    const int n = n0 + threadIdx.x % per, part_id = threadIdx.x / per;
+    const int jlen = p.E / parts, j0 = part_id * jlen;
+    float acc = 0.f;
+    if (n < blk.c_out) {
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll 8
-    for (int j = j0; j < j0 + jlen; j += 4) {
-      s0 = fmaf(__ldg(blk.weight + (size_t)(j + 0) * blk.c_out + n), emb[j + 0], s0);
-      s1 = fmaf(__ldg(blk.weight + (size_t)(j + 1) * blk.c_out + n), emb[j + 1], s1);
-      s2 = fmaf(__ldg(blk.weight + (size_t)(j + 2) * blk.c_out + n), emb[j + 2], s2);
-      s3 = fmaf(__ldg(blk.weight + (size_t)(j + 3) * blk.c_out + n), emb[j + 3], s3);
+      for (int j = j0; j < j0 + jlen; j += 4) {
+        s0 = fmaf(__ldg(blk.weight + (size_t)(j + 0) * blk.c_out + n), emb[j + 0], s0);
+        s1 = fmaf(__ldg(blk.weight + (size_t)(j + 1) * blk.c_out + n), emb[j + 1], s1);
+        s2 = fmaf(__ldg(blk.weight + (size_t)(j + 2) * blk.c_out + n), emb[j + 2], s2);
+        s3 = fmaf(__ldg(blk.weight + (size_t)(j + 3) * blk.c_out + n), emb[j + 3], s3);
+      }
+      acc = (s0 + s1) + (s2 + s3);
     }
-    acc = (s0 + s1) + (s2 + s3);
+    part[part_id][threadIdx.x % per] = acc;
+    __syncthreads();
+    const int nn = n0 + threadIdx.x;
+    if (threadIdx.x < per && nn < blk.c_out) {
+      float c = 1.0f;
+      for (int q = 0; q < parts; ++q) c += part[q][threadIdx.x];
+      cfull[nn] = c;
+      sq += c * c;
+    }
+    __syncthreads();
   }
-  part[part_id][n] = acc;
-  __syncthreads();
-  float c = 0.f;
-  const int nn = threadIdx.x;
-  if (nn < blk.c_out) {
-    c = 1.0f;
-    for (int q = 0; q < parts; ++q) c += part[q][nn];
-  }
-  float sq = c * c;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffff, sq, o);
   if (lane == 0) red[warp] = sq;
@@ -432,7 +438,7 @@ __global__ void __launch_bounds__(256) embed_kernel(const __grid_constant__ Embe
 #pragma unroll
   for (int w = 0; w < 8; ++w) tot += red[w];
   const float inv = rsqrtf(tot / (float)blk.c_out + 1e-8f);
-  if (nn < blk.c_out) blk.cvec[(size_t)img * blk.c_out + nn] = c * inv;
+  for (int nn = threadIdx.x; nn < blk.c_out; nn += blockDim.x) blk.cvec[(size_t)img * blk.c_out + nn] = cfull[nn] * inv;
 }
 
 int embed_validate(const TdxEmbedDesc& d) {
@@ -449,7 +455,7 @@ int embed_validate(const TdxEmbedDesc& d) {
                 d.noise_dims);
   }
   for (int b = 0; b < d.n_blocks; ++b)
-    TDX_REQUIRE(d.blocks[b].weight && d.blocks[b].cvec && d.blocks[b].c_out >= 1 && d.blocks[b].c_out <= 256,
+    TDX_REQUIRE(d.blocks[b].weight && d.blocks[b].cvec && d.blocks[b].c_out >= 1 && d.blocks[b].c_out <= 1024,
                 "embed: block %d invalid", b);
   return TDX_OK;
 }

@@ -44,8 +44,8 @@ constexpr int kMaxSB = 18;                        // B ring depth (max; also the
 constexpr int kAccCols = 256;                     // TMEM columns per accumulator buffer (2 buffers)
 constexpr int kEpiWarps = 8;
 constexpr int kThreads = 128 + 32 * kEpiWarps;
-constexpr int kMaxSplit = 4;
-constexpr int kSmemMisc = 8192;                   // barriers, TMEM slot, pixel-norm statistics
+constexpr int kMaxSplit = 8;                      // max CTAs (cluster size) sharing one M tile's pixel-norm statistics
+constexpr int kSmemMisc = 12288;                  // barriers, TMEM slot, pixel-norm statistics
 constexpr int kSmemBudget = 227 * 1024;
 
 struct IgemmParams {
@@ -743,7 +743,8 @@ static int ensure_scratch(float** ws, int** cnt) {
 //     reduce through an L2-resident fp32 workspace (only when every part fits on the chip at once).
 struct ItemShape { int ncta, resident, sb, ksplit; };
 
-static ItemShape choose_item_shape(int cout, int tiles, int stages, int chunks, int forced_n, bool allow_ksplit) {
+static ItemShape choose_item_shape(int cout, int tiles, int stages, int chunks, int forced_n, bool allow_ksplit,
+                                   bool norm_cluster = false) {
   if (!forced_n && getenv("TDX_IGEMM_N")) forced_n = atoi(getenv("TDX_IGEMM_N"));
   if (forced_n && (forced_n > cout || cout % forced_n)) forced_n = 0;
   int forced_k = getenv("TDX_IGEMM_KSPLIT") ? atoi(getenv("TDX_IGEMM_KSPLIT")) : 0;
@@ -753,6 +754,7 @@ static ItemShape choose_item_shape(int cout, int tiles, int stages, int chunks, 
   for (int n = 64; n <= 256 && n <= cout; n += 64) {
     if (cout % n) continue;
     if (forced_n && n != forced_n) continue;
+    if (norm_cluster && cout / n > kMaxSplit) continue;   // pixel-norm statistics travel inside one cluster
     const int stage_bytes = n * 128;
     const int nsplit = cout / n;
     const long items = (long)tiles * nsplit;
@@ -808,7 +810,7 @@ int igemm_launch(const TdxIgemmDesc& d, const CUtensorMap* tms, cudaStream_t str
   p.tiles_y = (d.height + kTileH - 1) / kTileH;
   const int tiles = p.tiles_x * p.tiles_y * d.n_img;
   const bool norm_split = needs_norm(d);
-  ItemShape shp = choose_item_shape(d.c_out, tiles, p.stages_per_item, chunks, d.n_per_item, !norm_split);
+  ItemShape shp = choose_item_shape(d.c_out, tiles, p.stages_per_item, chunks, d.n_per_item, !norm_split, norm_split);
   if (norm_split && d.c_out / shp.ncta == 1) shp = choose_item_shape(d.c_out, tiles, p.stages_per_item, chunks, shp.ncta, true);
   p.ncta = shp.ncta;
   p.resident = shp.resident;
@@ -867,8 +869,11 @@ int igemm_validate(const TdxIgemmDesc& d) {
     TDX_REQUIRE(d.a_taps[s] == 9 || d.a_taps[s] == 1, "igemm: a_taps[%d]=%d not 9 or 1", s, d.a_taps[s]);
   }
   TDX_REQUIRE(d.b_packed != nullptr, "igemm: b_packed is null");
-  TDX_REQUIRE(d.c_out >= 64 && d.c_out <= 64 * kMaxSplit && d.c_out % 64 == 0,
-              "igemm: c_out=%d must be a multiple of 64 <= %d", d.c_out, 64 * kMaxSplit);
+  TDX_REQUIRE(d.c_out >= 64 && d.c_out <= 2048 && d.c_out % 64 == 0, "igemm: c_out=%d must be a multiple of 64 <= 2048",
+              d.c_out);
+  if (needs_norm(d))
+    TDX_REQUIRE(d.c_out / d.n_per_item <= kMaxSplit, "igemm: pixel-norm over %d channels needs n_per_item >= %d",
+                d.c_out, d.c_out / kMaxSplit);
   TDX_REQUIRE(d.n_per_item >= 64 && d.n_per_item <= 256 && d.n_per_item % 64 == 0 && d.c_out % d.n_per_item == 0,
               "igemm: n_per_item=%d must be 64/128/192/256 and divide c_out=%d (use tdx_igemm_choose_n)", d.n_per_item,
               d.c_out);
@@ -907,7 +912,8 @@ extern "C" int tdx_igemm_choose_n(int32_t c_out, int32_t n_img, int32_t height, 
     chunks += a_channels[s] / 64;
   }
   const int tiles = ((width + tdx::kTileW - 1) / tdx::kTileW) * ((height + tdx::kTileH - 1) / tdx::kTileH) * n_img;
-  return tdx::choose_item_shape(c_out, tiles, stages, chunks, 0, true).ncta;
+  // conservative: assume the launch may need cluster-wide pixel-norm statistics (slices per tile <= cluster limit)
+  return tdx::choose_item_shape(c_out, tiles, stages, chunks, 0, true, true).ncta;
 }
 
 // Debug: the (n_per_item, ksplit, resident, ring depth) the launch heuristics pick for a shape.
@@ -920,7 +926,7 @@ extern "C" void tdx_debug_igemm_plan(int32_t c_out, int32_t n_img, int32_t heigh
     chunks += a_channels[s] / 64;
   }
   const int tiles = ((width + tdx::kTileW - 1) / tdx::kTileW) * ((height + tdx::kTileH - 1) / tdx::kTileH) * n_img;
-  tdx::ItemShape shp = tdx::choose_item_shape(c_out, tiles, stages, chunks, n_per_item, !needs_norm);
+  tdx::ItemShape shp = tdx::choose_item_shape(c_out, tiles, stages, chunks, n_per_item, !needs_norm, needs_norm != 0);
   if (needs_norm && c_out / shp.ncta == 1) shp = tdx::choose_item_shape(c_out, tiles, stages, chunks, shp.ncta, true);
   out4[0] = shp.ncta; out4[1] = shp.ksplit; out4[2] = shp.resident; out4[3] = shp.sb;
 }

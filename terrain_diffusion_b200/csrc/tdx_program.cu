@@ -14,9 +14,12 @@ int conv_out_validate(const TdxConvOutDesc& d);
 int conv_out_launch(const TdxConvOutDesc& d, cudaStream_t stream);
 int embed_validate(const TdxEmbedDesc& d);
 int direct_prepare();
+int attn_validate(const TdxAttnDesc& d);
+int attn_prepare();
+int attn_launch(const TdxAttnDesc& d, cudaStream_t stream);
 int embed_launch(const TdxEmbedDesc& d, cudaStream_t stream);
 
-enum OpType { OP_CONV_IN, OP_IGEMM, OP_CONV_OUT, OP_EMBED };
+enum OpType { OP_CONV_IN, OP_IGEMM, OP_CONV_OUT, OP_EMBED, OP_ATTN };
 
 struct Op {
   OpType type;
@@ -25,6 +28,7 @@ struct Op {
   TdxConvInDesc ci;
   TdxConvOutDesc co;
   TdxEmbedDesc em;
+  TdxAttnDesc at;
   std::vector<TdxEmbedBlock> blocks;
 };
 }  // namespace tdx
@@ -48,6 +52,7 @@ static int launch_all(TdxProgram* p, cudaStream_t stream) {
         op.em.blocks = op.blocks.data();
         rc = embed_launch(op.em, stream);
         break;
+      case OP_ATTN: rc = attn_launch(op.at, stream); break;
     }
     if (rc != TDX_OK) return rc;
   }
@@ -122,6 +127,19 @@ extern "C" int tdx_program_add_embed(TdxProgram* p, const TdxEmbedDesc* d) {
   return invalidate_graph(p);
 }
 
+extern "C" int tdx_program_add_attn(TdxProgram* p, const TdxAttnDesc* d) {
+  TDX_REQUIRE(p && d, "program_add_attn: null argument");
+  int rc = attn_validate(*d);
+  if (rc != TDX_OK) return rc;
+  rc = attn_prepare();
+  if (rc != TDX_OK) return rc;
+  Op op;
+  op.type = OP_ATTN;
+  op.at = *d;
+  p->ops.push_back(op);
+  return invalidate_graph(p);
+}
+
 extern "C" int tdx_program_num_launches(const TdxProgram* p) { return p ? (int)p->ops.size() : -1; }
 
 static int ensure_graph(TdxProgram* p) {
@@ -190,6 +208,7 @@ extern "C" int tdx_program_profile(TdxProgram* p, float* ms_per_launch, int32_t*
         op.em.blocks = op.blocks.data();
         rc = embed_launch(op.em, stream);
         break;
+      case OP_ATTN: rc = attn_launch(op.at, stream); break;
     }
     cudaEventRecord(ev[i + 1], stream);
     if (kinds) kinds[i] = (int32_t)op.type;

@@ -107,10 +107,13 @@ class FoldedWeights:
         self.clip = float(bk.get("clip_act", 256.0) or 0.0)
         self.cb = float(cfg.get("concat_balance", 0.3))
         self.enc, self.dec = enc, dec
+        self.cph = int(bk.get("channels_per_head", 64))
+        self.t_attn = float(bk.get("attn_balance", 0.3))
         for b in enc + dec:
-            if b.get("attention") and b["cout"] // bk.get("channels_per_head", 64):
-                raise NotImplementedError(f"self-attention block {b['name']} (base/latent model) is not implemented yet "
-                                          "on the B200 path (SURVEY.md section 8f, rank 1)")
+            b["heads"] = (b["cout"] // self.cph) if b.get("attention") else 0
+            if b["heads"] and self.cph != 64:
+                raise NotImplementedError(f"attention block {b['name']}: channels_per_head={self.cph}; the B200 path "
+                                          "implements the shipped value 64")
         self.mc = cfg.get("model_channels", 128)
         mults = cfg.get("model_channel_mults") or [1, 2, 3, 4]
         self.emb_channels = cfg.get("emb_channels") or self.mc * max(mults)
@@ -162,6 +165,16 @@ class FoldedWeights:
                 ws = effective_weight(sd[p + "conv_skip.weight"]) if (p + "conv_skip.weight") in sd else None
                 # effective GEMM operands as bf16 segment lists; packed per launch shape by packed()
                 seg = self.segs
+                if b["heads"]:
+                    # UNetBlock.attn (unet_block.py:102-108): qkv rows are (head, d, {q,k,v}) interleaved -> split into
+                    # three [C, C] projections with channel = head*64 + d; mp_sum(attn_balance) folded into proj.
+                    c = b["cout"]
+                    wqkv = effective_weight(sd[p + "attn_qkv.weight"]).reshape(b["heads"], self.cph, 3, c, 1, 1)
+                    for wi, nm in enumerate(("q", "k", "v")):
+                        seg[p + nm] = [wqkv[:, :, wi].reshape(c, c, 1, 1).contiguous().bfloat16()]
+                    ta = self.t_attn
+                    na = math.sqrt((1 - ta) ** 2 + ta ** 2)
+                    seg[p + "proj"] = [(effective_weight(sd[p + "attn_proj.weight"]) * (ta / na)).bfloat16()]
                 if b["mode"] == "enc":
                     if ws is not None:
                         seg[p + "k1"] = [ws.bfloat16()]
@@ -306,6 +319,44 @@ class UNetEmitter:
         d.n_img, d.height, d.width = self.n, h, w
         return d
 
+    def _finish_block(self, prog, d, b, key, cout, h, w, nxt, enc_index):
+        """Tail of UNetBlock.forward after conv_res1 (`d` = its launch, residual already configured):
+        [x = mp_sum(x, attn(x))] ; clip ; write what the consumers need (unet_block.py:147-156)."""
+        fw = self.fw
+        if not b["heads"]:
+            d.clip = fw.clip
+            cur = self._emit_outputs(d, key, cout, h, w, nxt, enc_index)
+            self._add_igemm(prog, d)
+            return cur
+        # ---- attention: x1 = mp_sum(x, y) un-clipped -> q, k, v (1x1) -> softmax core -> proj (1x1) + mp_sum + clip
+        x1 = self.act(key + "x1", cout, h, w)
+        d.clip = 0.0
+        self._set_out(d, 0, x1, L.OUT_RAW)
+        self._add_igemm(prog, d)
+        qkv = []
+        for nm in ("q", "k", "v"):
+            t = self.act(key + nm, cout, h, w)
+            dq = self._igemm(prog, [(x1, cout, 1)], key + nm, cout, h, w)
+            self._set_out(dq, 0, t, L.OUT_RAW)
+            self._add_igemm(prog, dq)
+            qkv.append(t)
+        yat = self.act(key + "attn_y", cout, h, w)
+        ad = L.TdxAttnDesc()
+        ad.q, ad.k, ad.v, ad.out = qkv[0].data_ptr(), qkv[1].data_ptr(), qkv[2].data_ptr(), yat.data_ptr()
+        ad.n_img, ad.heads, ad.head_dim, ad.tokens = self.n, b["heads"], fw.cph, h * w
+        L.check(L.lib().tdx_program_add_attn(prog.handle, C.byref(ad)))
+        prog.n_launch += 1
+        dp = self._igemm(prog, [(yat, cout, 1)], key + "proj", cout, h, w)
+        ta = fw.t_attn
+        dp.epi_flags = L.EPI_RESID
+        dp.resid = x1.data_ptr()
+        dp.resid_spatial = L.SP_SAME
+        dp.resid_scale = (1 - ta) / math.sqrt((1 - ta) ** 2 + ta ** 2)
+        dp.clip = fw.clip
+        cur = self._emit_outputs(dp, key, cout, h, w, nxt, enc_index)
+        self._add_igemm(prog, dp)
+        return cur
+
     def _add_igemm(self, prog, d):
         L.check(L.lib().tdx_program_add_igemm(prog.handle, C.byref(d)))
         prog.n_igemm += 1
@@ -412,9 +463,7 @@ class UNetEmitter:
                 d.resid_spatial = resid_sp
                 d.resid_pnorm = resid_pn
                 d.resid_scale = fw.w_skip
-                d.clip = fw.clip
-                cur = self._emit_outputs(d, key, cout, h, w, nxt, enc_index)
-                self._add_igemm(prog, d)
+                cur = self._finish_block(prog, d, b, key, cout, h, w, nxt, enc_index)
             else:
                 resid_sp = L.SP_SAME
                 if b["resample"] == "up":
@@ -442,9 +491,7 @@ class UNetEmitter:
                     d.resid = cur["raw"].data_ptr()
                     d.resid_spatial = resid_sp
                     d.resid_scale = fw.w_skip
-                d.clip = fw.clip
-                cur = self._emit_outputs(d, key, cout, h, w, nxt, None)
-                self._add_igemm(prog, d)
+                cur = self._finish_block(prog, d, b, key, cout, h, w, nxt, None)
             if side == "enc":
                 skips.append(cur)
 

@@ -103,6 +103,30 @@ def test_coarse_model_with_float_conditioning_matches_reference_golden():
     assert rel_rms(y, torch.from_numpy(G["coarse.y"])) < TOL
 
 
+def test_base_latent_model_with_attention_matches_reference_golden():
+    """the 253 M-parameter latent model (192..768 channels, tensor conditioning, one cosine
+    self-attention block at 8x8 tokens) vs the unmodified reference's fp32 output."""
+    cfg = dict(image_size=512, in_channels=5, out_channels=5, model_channels=192, model_channel_mults=[1, 2, 3, 4],
+               layers_per_block=3, attn_resolutions=[8, 16], midblock_attention=True, concat_balance=0.5,
+               conditional_inputs=[["tensor", 58, 1.0]], fourier_scale="pos", block_kwargs={"dropout": 0.1})
+    sd = ounet.procedural_state_dict(cfg, seed=0)
+    m = EDMUnet2D(**cfg).eval()
+    m.load_state_dict(sd)
+    del sd
+    m = m.cuda()
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(1, 5, 64, 64, generator=g)
+    t = torch.atan(torch.exp(torch.randn(1, generator=g) * 1.5) / 0.5)
+    cond = [torch.randn(1, 58, generator=g)]
+    y = m(x.cuda(), t.cuda(), [c.cuda() for c in cond]).cpu()
+    ref = torch.from_numpy(G["base.y"])
+    assert float(ref.std()) > 0.5
+    assert rel_rms(y, ref) < TOL
+    # batch of 4 tiles (the product's latent stage batches up to 16): rows must agree with the single-tile result
+    y4 = m(x.cuda().repeat(4, 1, 1, 1), t.cuda().repeat(4), [cond[0].cuda().repeat(4, 1)]).cpu()
+    assert rel_rms(y4[2:3], ref) < TOL
+
+
 # ------------------------------------------------------------------------------------------------ scheduler
 @pytest.mark.parametrize("n", [4, 12, 20])
 def test_scheduler_step_sequence_matches_reference_golden(n):
