@@ -183,6 +183,9 @@ int tdx_noise_patch(uint64_t base_seed, int64_t y0, int64_t x0, int32_t h, int32
                     int32_t tile_h, int32_t tile_w, float* out, void* workspace, int64_t workspace_bytes,
                     void* stream);
 int64_t tdx_noise_patch_workspace_bytes(int32_t channels, int32_t tile_h, int32_t tile_w);
+/* portable_rng.standard_normal(seed, n) (inference/portable_rng.py:77-82): one raw stream, bit-exact;
+ * workspace >= tdx_noise_patch_workspace_bytes(1, 1, n). */
+int tdx_standard_normal(uint64_t seed, int64_t n, float* out, void* workspace, int64_t workspace_bytes, void* stream);
 /* Synchronises `stream` and reports whether the last tdx_noise_patch on `workspace` completed its streams. */
 int tdx_noise_patch_status(void* workspace, void* stream);
 /* _tile_seed (world_pipeline.py:58-63): 64-bit seed of tile (ty, tx); host-side integer hash. */

@@ -221,6 +221,43 @@ extern "C" int tdx_noise_patch(uint64_t base_seed, int64_t y0, int64_t x0, int32
   return TDX_OK;
 }
 
+/* portable_rng.standard_normal(seed, n): ONE stream of n fp32 normals seeded directly with `seed` (no tile hash);
+ * workspace: tdx_noise_patch_workspace_bytes(1, 1, n) bytes. */
+extern "C" int tdx_standard_normal(uint64_t seed, int64_t n, float* out, void* workspace, int64_t workspace_bytes,
+                                   void* stream_) {
+  TDX_REQUIRE(out && workspace && n >= 1 && n < (1LL << 30), "standard_normal: bad arguments");
+  TDX_REQUIRE(workspace_bytes >= tdx_noise_patch_workspace_bytes(1, 1, (int32_t)n),
+              "standard_normal: workspace too small (%lld bytes)", (long long)workspace_bytes);
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  const long long n_pairs = pair_budget(n);
+  const long long n_chunks = (n_pairs + kChunk - 1) / kChunk;
+  int* status = reinterpret_cast<int*>(workspace);
+  int* counts = status + 64;
+  TDX_CHECK_CUDA(cudaMemsetAsync(status, 0, sizeof(int), stream));
+  NoiseEmit p;
+  p.seed = seed;
+  p.n_pairs = n_pairs;
+  p.n_out = n;
+  p.tile_h = 1;
+  p.tile_w = (int)n;
+  p.tile_y0 = 0;
+  p.tile_x0 = 0;
+  p.y0 = 0;
+  p.x0 = 0;
+  p.h = 1;
+  p.w = (int)n;
+  p.channels = 1;
+  p.out = out;
+  p.status = status;
+  const int threads = 128;
+  const int blocks = (int)((n_chunks + threads - 1) / threads);
+  noise_count_kernel<<<blocks, threads, 0, stream>>>(p.seed, n_pairs, counts);
+  noise_scan_kernel<<<1, 1024, 0, stream>>>(counts, n_chunks);
+  noise_emit_kernel<<<blocks, threads, 0, stream>>>(p, counts, n_chunks);
+  TDX_CHECK_CUDA(cudaGetLastError());
+  return TDX_OK;
+}
+
 /* Reads back the overflow flag written by the last tdx_noise_patch on this workspace (synchronises the stream). */
 extern "C" int tdx_noise_patch_status(void* workspace, void* stream_) {
   int st = 0;

@@ -5,3 +5,4 @@ from .samplers import (sample_decoder_consistency_tiled, sample_decoder_diffusio
 from .sharded import ShardedCanvas  # noqa: F401
 from .solve import DiffusionSolve  # noqa: F401
 from .tiling import linear_weight_window, padded_batch_size, shard_rows, tile_starts, window_range  # noqa: F401
+from .stages import coarse_stage_tile, decoder_stage_tile, latent_stage_tiles, process_latent_conditioning  # noqa: F401

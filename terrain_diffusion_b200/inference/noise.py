@@ -37,6 +37,15 @@ def gaussian_noise_patch(base_seed: int, y0: int, x0: int, h: int, w: int, chann
 
 
 def standard_normal(seed: int, n: int, device="cuda") -> torch.Tensor:
-    """portable_rng.standard_normal(seed, n) as a CUDA tensor: one stream of n normals from `seed`."""
-    # a 1 x n "tile" whose tile seed is `seed` itself cannot be expressed through tile_seed(); use the raw entry
-    raise NotImplementedError("use gaussian_noise_patch; raw streams are exposed for tests via tile geometry")
+    """portable_rng.standard_normal(seed, n) as an fp32 CUDA tensor (bit-identical stream)."""
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        raise L.TdxError("standard_normal (B200 path) generates on the GPU; there is no CPU path")
+    out = torch.empty((n,), dtype=torch.float32, device=dev)
+    if n == 0:
+        return out
+    nbytes = int(L.lib().tdx_noise_patch_workspace_bytes(1, 1, n))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    L.check(L.lib().tdx_standard_normal(int(seed) & MASK64, n, out.data_ptr(), ws.data_ptr(), nbytes,
+                                        L.current_stream_ptr()))
+    return out

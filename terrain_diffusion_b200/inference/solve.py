@@ -36,7 +36,14 @@ class DiffusionSolve:
         self.prog = UNetProgram()
         # the noise labels of all steps are known up front: ONE embed launch produces every step's modulation vectors
         em = UNetEmitter(fw, n, h, w, cvec_sets=num_steps)
-        em.emit_embed(self.prog, labels=self.labels.reshape(-1))
+        self.host_emb = len(model.conditional_layers) > 0 or not fw.pos_emb
+        if self.host_emb:
+            # conditional models (coarse: five float conditions): the 256-wide embeddings of all steps are computed
+            # by host torch ops per run() and handed to the embed launch
+            self.emb_all = torch.zeros((num_steps * n, fw.emb_channels), dtype=torch.float32, device=dev)
+            em.emit_embed(self.prog, emb_in=self.emb_all)
+        else:
+            em.emit_embed(self.prog, labels=self.labels.reshape(-1))
         for i in range(num_steps):
             srcs = [(self.sample, cs, self.c_in[i:i + 1])]
             if cc > 0:
@@ -46,9 +53,14 @@ class DiffusionSolve:
         self.launches_per_solve = self.prog.n_launch
 
     @torch.no_grad()
-    def run(self, noise: torch.Tensor, cond: torch.Tensor | None, use_graph: bool = True) -> torch.Tensor:
+    def run(self, noise: torch.Tensor, cond: torch.Tensor | None, use_graph: bool = True,
+            conditional_inputs=None) -> torch.Tensor:
         """noise: [n, Cs, h, w] initial sample (already scaled by sigma_0); returns the denoised sample (a view of the
         solver's state buffer -- copy it before the next run)."""
+        if self.host_emb:
+            embs = [self.model._host_embedding(self.labels[i], conditional_inputs or [])
+                    for i in range(self.num_steps)]
+            self.emb_all.copy_(torch.cat(embs, dim=0))
         self.sample.copy_(noise)
         if cond is not None:
             self.cond.copy_(cond)
