@@ -174,6 +174,11 @@ int tdx_sched_step(float* sample, const float* model_out, float* x0_prev, int64_
 int tdx_blend_accumulate(float* canvas_val, float* canvas_w, int32_t channels, int32_t canvas_h, int32_t canvas_w_px,
                          const float* tile, const float* window, int32_t tile_h, int32_t tile_w, int32_t y0,
                          int32_t x0, void* stream);
+/* dst[c, y0+y, x0+x] += tile[c, y, x] (fp32, clipped to dst): the window-sum of the reference's canvas engine
+ * (infinite_tensor: "sums overlapping window outputs", annotated_infinite_panorama.py:141-146) for tiles that are
+ * already packed as (x*w, w). */
+int tdx_canvas_add(float* dst, int32_t channels, int32_t dst_h, int32_t dst_w, const float* tile, int32_t tile_h,
+                   int32_t tile_w, int32_t y0, int32_t x0, void* stream);
 /* out = canvas_val / canvas_w [/ divisor]   (normalise-on-read, world_pipeline.py:1223,1301; the bounded samplers
  * divide by sigma_data afterwards, sample_diffusion_decoder.py:211).  divisor == 1 skips the second division. */
 int tdx_blend_normalize(float* out, const float* canvas_val, const float* canvas_w, int32_t channels, int64_t plane,

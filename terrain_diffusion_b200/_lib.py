@@ -109,6 +109,9 @@ def _declare(l: C.CDLL) -> None:
     l.tdx_blend_accumulate.restype = C.c_int
     l.tdx_blend_accumulate.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                                        C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
+    l.tdx_canvas_add.restype = C.c_int
+    l.tdx_canvas_add.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32,
+                                 C.c_int32, C.c_int32, C.c_void_p]
     l.tdx_blend_normalize.restype = C.c_int
     l.tdx_blend_normalize.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_float,
                                       C.c_void_p]

@@ -507,6 +507,19 @@ __global__ void blend_accumulate_kernel(float* cval, float* cw, int channels, in
   cw[cidx] = __fadd_rn(cw[cidx], w);
 }
 
+__global__ void canvas_add_kernel(float* dst, int channels, int DH, int DW, const float* tile, int th, int tw, int y0,
+                                  int x0) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y;
+  if (x >= tw) return;
+  const int Y = y0 + y, X = x0 + x;
+  if (Y < 0 || Y >= DH || X < 0 || X >= DW) return;
+  for (int c = 0; c < channels; ++c) {
+    const size_t di = ((size_t)c * DH + Y) * DW + X;
+    dst[di] = __fadd_rn(dst[di], tile[((size_t)c * th + y) * tw + x]);
+  }
+}
+
 __global__ void blend_normalize_kernel(float* out, const float* cval, const float* cw, int channels, int64_t plane,
                                        float divisor) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -563,6 +576,17 @@ extern "C" int tdx_blend_accumulate(float* canvas_val, float* canvas_w, int32_t 
   dim3 grid((tile_w + 127) / 128, tile_h);
   blend_accumulate_kernel<<<grid, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       canvas_val, canvas_w, channels, canvas_h, canvas_w_px, tile, window, tile_h, tile_w, y0, x0);
+  TDX_CHECK_CUDA(cudaGetLastError());
+  return TDX_OK;
+}
+
+extern "C" int tdx_canvas_add(float* dst, int32_t channels, int32_t dst_h, int32_t dst_w, const float* tile,
+                              int32_t tile_h, int32_t tile_w, int32_t y0, int32_t x0, void* stream) {
+  TDX_REQUIRE(dst && tile && channels >= 1 && dst_h >= 1 && dst_w >= 1 && tile_h >= 1 && tile_w >= 1,
+              "canvas_add: bad arguments");
+  dim3 grid((tile_w + 127) / 128, tile_h);
+  canvas_add_kernel<<<grid, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(dst, channels, dst_h, dst_w, tile,
+                                                                             tile_h, tile_w, y0, x0);
   TDX_CHECK_CUDA(cudaGetLastError());
   return TDX_OK;
 }

@@ -1,0 +1,108 @@
+"""Lazy unbounded canvas (infinite_tensor semantics) and the three-stage pipeline wiring."""
+import math
+
+import pytest
+import torch
+
+from oracle import unet as ounet
+from terrain_diffusion_b200.inference import LazyCanvas, TensorWindow, TerrainPipeline, decoder_stage_tile
+from terrain_diffusion_b200.inference.tiling import linear_weight_window, window_range
+from terrain_diffusion_b200.models import EDMUnet2D
+from tests.test_oracle_golden import BASE_CFG, COARSE_CFG
+
+pytestmark = pytest.mark.gpu
+
+
+def _tile(i, j, c, t):
+    g = torch.Generator().manual_seed((i + 1000) * 100003 + (j + 1000))
+    return torch.randn(c, t, t, generator=g)
+
+
+def _brute(a, b, c, d, ch, size, stride, off):
+    """Sum over every window intersecting the slice, row-major, fp32 -- straight from the Appendix C definition."""
+    out = torch.zeros(ch, b - a, d - c)
+    for i in window_range(a, b, size, stride, off):
+        for j in window_range(c, d, size, stride, off):
+            t = _tile(i, j, ch, size)
+            y0, x0 = i * stride + off, j * stride + off
+            ys, ye, xs, xe = max(a, y0), min(b, y0 + size), max(c, x0), min(d, x0 + size)
+            out[:, ys - a:ye - a, xs - c:xe - c] += t[:, ys - y0:ye - y0, xs - x0:xe - x0]
+    return out
+
+
+@pytest.mark.parametrize("size,stride,off", [(64, 48, 0), (64, 32, 0), (16, 16, -5)])
+def test_lazy_canvas_equals_bruteforce_window_sum_incl_negative_coordinates(size, stride, off):
+    calls = []
+
+    def f(ctx):
+        calls.append(ctx)
+        return _tile(ctx[1], ctx[2], 3, size).cuda()
+
+    cv = LazyCanvas(3, f, TensorWindow((3, size, size), (3, stride, stride), (0, off, off)), "cuda", block=128)
+    for k, (a, b, c, d) in enumerate([(-70, 95, -130, 20), (0, 64, 0, 64), (100, 101, -3, 300)]):
+        got = cv[:, a:b, c:d].cpu()
+        want = _brute(a, b, c, d, 3, size, stride, off)
+        if k == 0:
+            assert torch.equal(got, want), (a, b, c, d)   # same (row-major) order of fp32 additions: bit-identical
+        else:
+            # windows cached by earlier requests were added in THAT request's order: equal up to fp32 re-association
+            assert torch.allclose(got, want, rtol=0, atol=2e-6), (a, b, c, d)
+    n = len(calls)
+    cv[:, 0:64, 0:64]                      # cached: no window is computed twice
+    assert len(calls) == n and len(set(calls)) == n
+
+
+def test_dependency_windows_use_the_same_window_index_and_batches():
+    """latent <- coarse wiring of the reference: size 4, stride 1, offset -1 (world_pipeline.py:1147)."""
+    base = LazyCanvas(1, lambda ctx: torch.full((1, 8, 8), float(ctx[1] * 100 + ctx[2])).cuda(),
+                      TensorWindow((1, 8, 8), (1, 8, 8)), "cuda", block=64)
+    seen = {}
+
+    def f(ctxs, deps):
+        assert isinstance(ctxs, list) and len(ctxs) <= 3
+        outs = []
+        for ctx, dep in zip(ctxs, deps):
+            seen[ctx] = dep.clone()
+            outs.append(torch.ones(1, 4, 4, device="cuda"))
+        return outs
+
+    top = LazyCanvas(1, f, TensorWindow((1, 4, 4), (1, 2, 2)), "cuda", args=(base,),
+                     args_windows=(TensorWindow((1, 4, 4), (1, 1, 1), (0, -1, -1)),), batch_size=3, block=64)
+    top[:, 0:6, 0:6]
+    for (_, i, j), dep in seen.items():
+        assert torch.equal(dep, base[:, i - 1:i + 3, j - 1:j + 3])
+
+
+def test_three_stage_pipeline_slice_equals_direct_stage_evaluation():
+    def build(cfg):
+        m = EDMUnet2D(**cfg).eval()
+        m.load_state_dict(ounet.procedural_state_dict(cfg, seed=0))
+        return m.cuda()
+
+    coarse, base, dec = build(COARSE_CFG), build(BASE_CFG), build(ounet.DECODER_CFG)
+    g = torch.Generator().manual_seed(3)
+
+    def cond_fn(i1, i2, j1, j2):
+        gg = torch.Generator().manual_seed(i1 * 7919 + j1 + 12345)
+        return torch.randn(5, i2 - i1, j2 - j1, generator=gg)
+
+    pipe = TerrainPipeline(coarse, base, dec, seed=7, conditioning_fn=cond_fn,
+                           coarse_means=(torch.randn(6, generator=g) * 0.1).tolist(),
+                           coarse_stds=(torch.rand(6, generator=g) + 0.5).tolist(), cond_snr=[0.3, 0.5, 1.0, 2.0, 4.0],
+                           histogram_raw=torch.randn(5, generator=g), latents_means=torch.zeros(7),
+                           latents_stds=torch.ones(7), decoder_tile_size=128, decoder_tile_stride=96)
+    out = pipe.residual[:, 40:90, -20:70]          # rows: decoder window 0 only; columns: windows -1 and 0
+    assert out.shape == (2, 50, 90) and torch.isfinite(out).all() and float(out[1].min()) > 0
+    # the decoder window (0,0,0) recomputed directly from the blended latent canvas must be what the canvas summed
+    lat = pipe.latents[:, 0:16, 0:16]
+    t0 = decoder_stage_tile(dec, 7, (0, 0, 0), lat, linear_weight_window(128, "cuda"), [pipe.t_init], 128, 96)
+    lat_m1 = pipe.latents[:, 0:16, -12:4]
+    t1 = decoder_stage_tile(dec, 7, (0, 0, -1), lat_m1, linear_weight_window(128, "cuda"), [pipe.t_init], 128, 96)
+    # summation order in the canvas is row-major over window indices: (0,-1) then (0,0)
+    ref = torch.zeros(2, 50, 90, device="cuda")
+    ref[:, :, :52] += t1[:, 40:90, 76:128]         # window -1 covers columns [-96,32)
+    ref[:, :, 20:] += t0[:, 40:90, 0:70]           # window 0 covers columns [0,128)
+    assert torch.equal(out, ref)
+    assert pipe.coarse.windows_computed >= 1 and pipe.latents_init.windows_computed > pipe.latents.windows_computed
+    n = pipe.residual_normalized(40, -20, 90, 70)
+    assert torch.isfinite(n).all()
