@@ -72,6 +72,7 @@ struct IgemmParams {
   float resid_scale, clip;
   TdxOutSpec out[3];
   int dbg;                    // debug experiment flags (tools/trace_igemm.py), normally 0
+  unsigned long long* timeline;  // debug: [2] = {first CTA start, last CTA end} in globaltimer ns, normally null
   unsigned long long* trace;  // debug: per-item phase timestamps of CTA 0 (tools/trace_igemm.py), normally null
 };
 
@@ -213,6 +214,11 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CU
   const int warp = threadIdx.x >> 5;   // warp-uniform role id
   const int lane = threadIdx.x & 31;
   if (p.trace && blockIdx.x == 0 && threadIdx.x == 0) p.trace[126] = clock64();
+  if (p.timeline && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    atomicMin(p.timeline, t);
+  }
 
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&tm0);
@@ -513,18 +519,31 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CU
           rplane = (size_t)Hr * Wr;
           rbase = p.resid + ((size_t)img * C8) * rplane + (size_t)Yr * Wr + Xr;
           if (p.resid_pnorm) {
-            // the residual's pixel-norm runs over ALL Cout channels (every item reads them; L2-resident)
+            // the residual's pixel-norm runs over ALL Cout channels (every item reads them; L2-resident);
+            // 8 independent 16-byte loads in flight per step (C8 is a multiple of 8)
             float ss = 0.f;
-            for (int g = 0; g < C8; ++g) {
-              uint4 u = __ldg(rbase + g * rplane);
-              float a, b;
-              unpack_bf16x2(u.x, a, b); ss = fmaf(a, a, fmaf(b, b, ss));
-              unpack_bf16x2(u.y, a, b); ss = fmaf(a, a, fmaf(b, b, ss));
-              unpack_bf16x2(u.z, a, b); ss = fmaf(a, a, fmaf(b, b, ss));
-              unpack_bf16x2(u.w, a, b); ss = fmaf(a, a, fmaf(b, b, ss));
+            for (int g0 = 0; g0 < C8; g0 += 8) {
+              uint4 u[8];
+#pragma unroll
+              for (int g = 0; g < 8; ++g) u[g] = __ldg(rbase + (size_t)(g0 + g) * rplane);
+#pragma unroll
+              for (int g = 0; g < 8; ++g) {
+                float a, b;
+                unpack_bf16x2(u[g].x, a, b); ss = fmaf(a, a, fmaf(b, b, ss));
+                unpack_bf16x2(u[g].y, a, b); ss = fmaf(a, a, fmaf(b, b, ss));
+                unpack_bf16x2(u[g].z, a, b); ss = fmaf(a, a, fmaf(b, b, ss));
+                unpack_bf16x2(u[g].w, a, b); ss = fmaf(a, a, fmaf(b, b, ss));
+              }
             }
             rscale = p.resid_scale / (1e-4f + sqrtf(ss / (float)p.cout));
           }
+        }
+        // prefetch the residual values of this warp's first chunk while the MMAs are still running
+        uint4 rpre[4] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+        if ((p.epi & TDX_EPI_RESID) && valid && half < nchunks) {
+          const uint4* rptr = rbase + (size_t)((chbase >> 3) + half * 4) * rplane;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) rpre[g] = __ldg(rptr + (size_t)g * rplane);
         }
         OutCtx oc[3];
 #pragma unroll
@@ -572,7 +591,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CU
             const uint4* rptr = rbase + (size_t)((chbase >> 3) + ck * 4) * rplane;
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
-              uint4 u = valid ? __ldg(rptr + (size_t)g * rplane) : make_uint4(0, 0, 0, 0);
+              uint4 u = (ck == half) ? rpre[g] : (valid ? __ldg(rptr + (size_t)g * rplane) : make_uint4(0, 0, 0, 0));
               float rr[8];
               unpack_bf16x2(u.x, rr[0], rr[1]);
               unpack_bf16x2(u.y, rr[2], rr[3]);
@@ -687,10 +706,17 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CU
     tmem_dealloc(tmem_base, 512);
   }
   if (p.trace && blockIdx.x == 0 && threadIdx.x == 96) p.trace[125] = clock64();
+  if (p.timeline && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    atomicMax(p.timeline + 1, t);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------- host side
 static unsigned long long* g_trace_ptr = nullptr;
+static unsigned long long* g_timeline_ptr = nullptr;   // debug: consecutive launches fill consecutive [start,end] pairs
+static int g_timeline_idx = 0, g_timeline_cap = 0;
 static int g_dbg_flags = 0;
 
 static int ensure_scratch(float** ws, int** cnt);
@@ -835,6 +861,7 @@ int igemm_launch(const TdxIgemmDesc& d, const CUtensorMap* tms, cudaStream_t str
   for (int o = 0; o < 3; ++o) p.out[o] = d.out[o];
   p.trace = g_trace_ptr;
   p.dbg = g_dbg_flags;
+  p.timeline = (g_timeline_ptr && g_timeline_idx < g_timeline_cap) ? g_timeline_ptr + 2 * (g_timeline_idx++) : nullptr;
 
   int rc_prep = igemm_prepare();
   if (rc_prep != TDX_OK) return rc_prep;
@@ -902,6 +929,13 @@ extern "C" void tdx_debug_set_igemm_trace(void* device_u64x128) {
   tdx::g_trace_ptr = reinterpret_cast<unsigned long long*>(device_u64x128);
 }
 extern "C" void tdx_debug_set_igemm_flags(int flags) { tdx::g_dbg_flags = flags; }
+// Debug: every igemm launch recorded from now on writes {first CTA start, last CTA end} (globaltimer ns) into the next
+// slot of `device_u64_pairs` (pre-filled with {~0, 0}); pass null to stop.
+extern "C" void tdx_debug_set_igemm_timeline(void* device_u64_pairs, int capacity) {
+  tdx::g_timeline_ptr = reinterpret_cast<unsigned long long*>(device_u64_pairs);
+  tdx::g_timeline_idx = 0;
+  tdx::g_timeline_cap = capacity;
+}
 
 extern "C" int tdx_igemm_choose_n(int32_t c_out, int32_t n_img, int32_t height, int32_t width,
                                   const int32_t* a_channels, const int32_t* a_taps, int32_t n_seg) {

@@ -23,7 +23,7 @@ def main():
     flags = int(sys.argv[1]) if len(sys.argv) > 1 else 0
     lib.tdx_debug_set_igemm_flags(flags)
     print('### debug flags', flags)
-    for name, segs, cout, res in SHAPES:
+    for name, segs, cout, res in SHAPES + [("RES1 64->64 @256 (resid pnorm, 3 outputs)", [(64, 9)], 64, 256)]:
         acts = [to_nc8hw8(torch.randn(1, c, res, res, device=dev)) for c, _ in segs]
         wts = [torch.randn(cout, c, 3, 3, device=dev) * 0.02 for c, t in segs]
         n_item = L.igemm_choose_n(cout, 1, res, res, segs)
@@ -37,6 +37,12 @@ def main():
         d.n_img, d.height, d.width = 1, res, res
         d.epi_flags = L.EPI_EMB_SILU; d.cvec = cvec.data_ptr()
         d.out[0].ptr = out.data_ptr(); d.out[0].kind = L.OUT_RAW; d.out[0].scale = 1.0
+        if name.startswith("RES1"):
+            resid = to_nc8hw8(torch.randn(1, cout, res, res, device=dev))
+            out2 = torch.empty_like(out); out3 = torch.empty_like(out)
+            d.epi_flags = L.EPI_RESID; d.resid = resid.data_ptr(); d.resid_pnorm = 1; d.resid_scale = 0.9; d.clip = 256.0
+            d.out[1].ptr = out2.data_ptr(); d.out[1].kind = L.OUT_PNORM_SILU; d.out[1].scale = 1.0
+            d.out[2].ptr = out3.data_ptr(); d.out[2].kind = L.OUT_SILU; d.out[2].scale = 0.8
         for _ in range(2):
             L.check(lib.tdx_igemm_run(C.byref(d), L.current_stream_ptr()))
         torch.cuda.synchronize()
@@ -48,7 +54,7 @@ def main():
         t = trace.cpu().tolist()
         t0 = t[127]
         print(f"== {name}: clocks relative to CTA-0 setup done; kernel entry at {t[126]-t0}, exit at {t[125]-t0}")
-        for it in range(2):
+        for it in range(4):
             row = t[it * 8: it * 8 + 7]
             if row[0] == 0 and row[1] == 0:
                 break
