@@ -58,14 +58,13 @@ struct IgemmParams {
   int SB;                     // B ring depth
   int b_stage_bytes;          // ncta * 128
   int resident;               // the whole weight set of an item fits the ring: loaded once per CTA, reused by every item
-  int ksplit;                 // split-K: the K loop (64-channel chunks) of a work item is shared by ksplit CTAs
-  int chunks_total;           // sum of seg_chunks
-  float* ws;                  // split-K fp32 partial accumulators [group][ksplit-1][ncta][128]
-  int* ws_count;              // split-K arrival counters [group]
+  int ksplit;                 // split-K: the (chunk, tap) stages of a work item are shared by the ksplit CTAs of a cluster
+  float* ws;                  // split-K fp32 partial sums [group][dst part][ksplit-1 sources][ncta/ksplit cols][128 pixels]
   int H, W, nimg, tiles_x, tiles_y, num_items;
   int stages_per_item;
   int epi;
-  int cluster_stats;          // pixel-norm statistics are exchanged across the nsplit CTAs of a cluster
+  int cluster_stats;          // pixel-norm statistics are exchanged across the xsplit CTAs of a cluster
+  int xsplit;                 // CTAs that together hold all Cout channels of an M tile (= cluster size when cluster_stats)
   const float* cvec;
   const uint4* resid;
   int resid_spatial, resid_pnorm;
@@ -76,26 +75,23 @@ struct IgemmParams {
   unsigned long long* trace;  // debug: per-item phase timestamps of CTA 0 (tools/trace_igemm.py), normally null
 };
 
-// Flat 64-channel chunk index f (over all segments) -> (segment, chunk in segment); [f0, f1) = this CTA's K range.
-__device__ __forceinline__ void chunk_range(const IgemmParams& p, int item, int& f0, int& f1) {
+// K is walked in "stages" (one tap of one 64-channel chunk, in packed-weight order); [s0, s1) = this CTA's share.
+__device__ __forceinline__ void stage_range(const IgemmParams& p, int item, int& s0, int& s1) {
   const int k = item % p.ksplit;
-  f0 = (p.chunks_total * k) / p.ksplit;
-  f1 = (p.chunks_total * (k + 1)) / p.ksplit;
+  s0 = (p.stages_per_item * k) / p.ksplit;
+  s1 = (p.stages_per_item * (k + 1)) / p.ksplit;
 }
-__device__ __forceinline__ void chunk_seg(const IgemmParams& p, int f, int& seg, int& ch) {
-  seg = 0;
-  ch = f;
-  if (ch >= p.seg_chunks[0]) { ch -= p.seg_chunks[0]; seg = 1; }
-  if (seg == 1 && ch >= p.seg_chunks[1]) { ch -= p.seg_chunks[1]; seg = 2; }
-}
-__device__ __forceinline__ int stages_before(const IgemmParams& p, int f) {
-  int n = 0, rem = f;
-  for (int s = 0; s < p.nseg && rem > 0; ++s) {
-    const int c = rem < p.seg_chunks[s] ? rem : p.seg_chunks[s];
-    n += c * p.seg_taps[s];
-    rem -= c;
+// flat stage index -> (segment, chunk in segment, tap, taps of that segment)
+__device__ __forceinline__ void stage_locate(const IgemmParams& p, int s, int& seg, int& ch, int& tap, int& taps) {
+  int base = 0;
+  for (seg = 0;; ++seg) {
+    taps = p.seg_taps[seg];
+    const int n = p.seg_chunks[seg] * taps;
+    if (s < base + n || seg == p.nseg - 1) break;
+    base += n;
   }
-  return n;
+  ch = (s - base) / taps;
+  tap = (s - base) - ch * taps;
 }
 
 #define TDX_TRACE(slot, it)                                                                  \
@@ -178,12 +174,6 @@ __device__ __forceinline__ void store_group(const OutCtx& o, int group, const fl
   }
 }
 
-__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
-  int v;
-  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-
 __device__ __forceinline__ void load_acc32(uint32_t taddr, float (&v)[32]) {
   uint32_t r[32];
   tmem_ld32(taddr, r);
@@ -237,7 +227,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CU
     for (int i = 0; i < 2; ++i) {
       mbar_init(&t_full[i], 1);
       mbar_init(&t_empty[i], kEpiWarps);
-      mbar_init(&x_full[i], p.nsplit > 1 ? (p.nsplit - 1) * 128 : 1);
+      mbar_init(&x_full[i], p.xsplit > 1 ? (p.xsplit - 1) * 128 : 1);
     }
     fence_mbar_init();
   }
@@ -264,11 +254,11 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CU
       int split, img, Y0, X0;
       decode_item(p, item, split, img, Y0, X0);
       if (lane == 0) TDX_TRACE(0, it);
-      int f0, f1;
-      chunk_range(p, item, f0, f1);
-      for (int f = f0; f < f1; ++f) {
-        int seg, ch;
-        chunk_seg(p, f, seg, ch);
+      int s0, s1;
+      stage_range(p, item, s0, s1);
+      for (int s = s0; s < s1;) {
+        int seg, ch, tap, taps;
+        stage_locate(p, s, seg, ch, tap, taps);
         const CUtensorMap* tm = seg == 0 ? &tm0 : (seg == 1 ? &tm1 : &tm2);
         mbar_wait(&a_empty[sa], ph ^ 1, 100 + sa);
         if (elect_one()) {
@@ -277,8 +267,10 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CU
         }
         __syncwarp();
         if (++sa == kSA) { sa = 0; ph ^= 1; }
+        s += taps - tap;   // the rest of this chunk's taps use the same patch
       }
     }
+    if (p.ksplit > 1) cluster_sync_all();   // split-K hand-over barrier (see the epilogue)
   } else if (warp == 1) {
     // ------------------------------------------------------------------ B producer (pre-packed weight stages)
     // Weights are constants: no dependency on the previous kernel, so this starts streaming during its tail.
@@ -286,9 +278,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CU
     uint32_t ph = 0;
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
       const int split = (item / p.ksplit) % p.nsplit;   // constant per CTA: gridDim.x is a multiple of nsplit*ksplit
-      int f0, f1;
-      chunk_range(p, item, f0, f1);
-      const int st0 = stages_before(p, f0), st1 = stages_before(p, f1);
+      int st0, st1;
+      stage_range(p, item, st0, st1);
       const uint8_t* bsrc = reinterpret_cast<const uint8_t*>(p.B) +
                             ((size_t)split * p.stages_per_item + st0) * p.b_stage_bytes;
       for (int ks = 0; ks < st1 - st0; ++ks) {
@@ -307,6 +298,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CU
       }
       if (p.resident) break;   // the ring now holds this CTA's whole weight slice for every later item
     }
+    if (p.ksplit > 1) cluster_sync_all();
   } else if (warp == 2) {
     // ------------------------------------------------------------------ MMA issuer (one elected lane issues)
     const uint32_t idesc = make_idesc_bf16(128, p.ncta);
@@ -333,18 +325,19 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CU
       const uint32_t d_tmem = tmem_base + acc * kAccCols;
       const bool steady = p.resident && it > 0;   // weights already in the ring: no per-stage handshakes
       uint32_t accumulate = 0;
-      int f0, f1;
-      chunk_range(p, item, f0, f1);
+      int s0, s1;
+      stage_range(p, item, s0, s1);
       {
-        for (int f = f0; f < f1; ++f) {
-          int seg, ch;
-          chunk_seg(p, f, seg, ch);
-          const int taps = p.seg_taps[seg];
+        for (int s = s0; s < s1;) {
+          int seg, ch, tap0, taps;
+          stage_locate(p, s, seg, ch, tap0, taps);
+          const int tap1 = (taps - tap0 < s1 - s) ? taps : tap0 + (s1 - s);
           mbar_wait(&a_full[sa], pha, 400 + sa);
           tc_fence_after();
-          if (lane == 0 && f == f0) TDX_TRACE(2, it);
+          if (lane == 0 && s == s0) TDX_TRACE(2, it);
+          s += tap1 - tap0;
           const uint32_t a16 = a_ring16 + sa * (kAStageBytes >> 4);
-          if (steady && taps == 9) {
+          if (steady && taps == 9 && tap0 == 0 && tap1 == 9) {
             // ---- 36 MMAs back to back
             const uint32_t b16 = b_ring16 + sb * b_stage16;
             if (elect_one()) {
@@ -363,7 +356,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CU
             sb += 9;   // resident ring: SB == stages_per_item, a chunk's 9 stages never wrap
             if (sb >= p.SB) { sb -= p.SB; phb ^= 1; }
           } else {
-            for (int tap = 0; tap < taps; ++tap) {
+            for (int tap = tap0; tap < tap1; ++tap) {
               const uint32_t tapoff = taps == 9 ? (uint32_t)((tap / 3) * kPatchW + (tap % 3)) : (uint32_t)(kPatchW + 1);
               const uint32_t b16 = b_ring16 + sb * b_stage16;
               if (!steady) {
@@ -393,6 +386,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CU
       __syncwarp();
       if (lane == 0) TDX_TRACE(3, it);
     }
+    if (p.ksplit > 1) cluster_sync_all();
+  } else if (warp == 3) {
+    if (p.ksplit > 1) cluster_sync_all();
   } else if (warp >= 4 && !(p.dbg & 8)) {
     // ------------------------------------------------------------------ epilogue (TMEM -> registers -> global)
     // warp w and w+4 share TMEM lane quadrant (w & 3); the item's 32-column chunks alternate between the two.
@@ -402,7 +398,6 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CU
     const int m = q * 32 + lane;
     const int y = m >> 3, x = m & 7;
     const int C8 = p.cout >> 3;
-    const int nchunks = p.ncta >> 5;
     const bool need_norm = (p.epi & TDX_EPI_PNORM) || p.out[0].kind == TDX_OUT_PNORM_SILU ||
                            p.out[1].kind == TDX_OUT_PNORM_SILU || p.out[2].kind == TDX_OUT_PNORM_SILU;
     const bool fast_res0 = (p.epi == TDX_EPI_EMB_SILU) && p.clip <= 0.f && p.out[0].kind == TDX_OUT_RAW &&
@@ -417,51 +412,47 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CU
       decode_item(p, item, split, img, Y0, X0);
       const int Y = Y0 + y, X = X0 + x;
       const bool valid = (Y < p.H) && (X < p.W);
-      const int chbase = split * p.ncta;                  // first output channel of this item
       const uint32_t taddr = tmem_base + acc * kAccCols + ((uint32_t)(q * 32) << 16);
-      const float* cvb = p.cvec ? p.cvec + (size_t)img * p.cout + chbase : nullptr;
 
-      // ---------------- split-K: ksplit CTAs each hold a partial sum of the same output tile.  Parts 1.. publish their
-      // fp32 accumulator through an L2-resident workspace; part 0 adds them and runs the epilogue.  (Launches with
-      // ksplit > 1 have one item per CTA and at most one CTA per SM, so all parts are co-resident.)
-      const int kpart = item % p.ksplit, group = item / p.ksplit;
-      float* wsg = p.ws + (size_t)group * (p.ksplit - 1) * p.ncta * 128;
-      if (p.ksplit > 1 && kpart > 0) {
+      // ---------------- split-K: the ksplit CTAs of a cluster each hold a partial sum of the same 128 x ncta tile.
+      // Reduce-scatter through an L2-resident fp32 workspace: every part publishes the column slices the other parts
+      // own, the cluster barrier (release/acquire, all warps of all parts take it once) hands them over, and each part
+      // finishes the epilogue of its own ncta/ksplit columns.  (Launches with ksplit > 1 have one item per CTA.)
+      int nchunks = p.ncta >> 5;   // 32-column chunks this CTA finalises
+      int col0 = 0;                // first accumulator column this CTA finalises
+      const float* red_src = nullptr;
+      int red_stride = 0;
+      if (p.ksplit > 1) {
+        const int ks = p.ksplit, kpart = item % ks, group = item / ks;
+        const int slice = p.ncta / ks, sch = slice >> 5;
+        float* wsg = p.ws + (size_t)group * (ks - 1) * p.ncta * 128;   // [dst part][source slot][slice cols][128]
         mbar_wait(&t_full[acc], accph, 600 + acc);
         tc_fence_after();
-        float* dst = wsg + (size_t)(kpart - 1) * p.ncta * 128 + m;
+        if (warp == 4 && lane == 0) TDX_TRACE(7, it);
         for (int ck = half; ck < nchunks; ck += 2) {
+          const int dst = ck / sch;
+          if (dst == kpart) continue;
+          const int slot = kpart - (kpart > dst ? 1 : 0);
+          float* d = wsg + ((size_t)(dst * (ks - 1) + slot) * slice + (size_t)(ck - dst * sch) * 32) * 128 + m;
           float v[32];
           __syncwarp();
           load_acc32(taddr + ck * 32, v);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) __stcg(dst + (size_t)(ck * 32 + j) * 128, v[j]);
+          for (int j = 0; j < 32; ++j) __stcg(d + (size_t)j * 128, v[j]);
         }
-        __threadfence();
-        named_bar_sync(9, 32 * kEpiWarps);
-        if (warp == 4 && lane == 0) atomicAdd(p.ws_count + group, 1);
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&t_empty[acc]);
-        continue;
+        cluster_sync_all();
+        nchunks = sch;
+        col0 = kpart * slice;
+        red_src = wsg + (size_t)kpart * (ks - 1) * slice * 128 + m;
+        red_stride = slice * 128;
       }
-      if (p.ksplit > 1) {
-        if (warp == 4 && lane == 0) {
-          long long t0 = clock64();
-          while (ld_acquire_gpu(p.ws_count + group) < p.ksplit - 1) {
-            if (clock64() - t0 > TDX_WAIT_LIMIT) {
-              printf("tdx: split-K partials wait timeout block=%d\n", (int)blockIdx.x);
-              __trap();
-            }
-          }
-          p.ws_count[group] = 0;   // ready for the next launch
-        }
-        named_bar_sync(9, 32 * kEpiWarps);
-      }
-      // adds the other parts' partial sums to accumulator chunk ck (no-op without split-K)
+      const int chbase = split * p.ncta + col0;           // first output channel this CTA writes
+      const uint32_t taddr_e = taddr + col0;
+      const float* cvb = p.cvec ? p.cvec + (size_t)img * p.cout + chbase : nullptr;
+      // adds the other parts' partial sums to this CTA's chunk ck (no-op without split-K)
       auto add_partials = [&](int ck, float (&v)[32]) {
         for (int kp = 0; kp < p.ksplit - 1; ++kp) {
-          const float* src = wsg + (size_t)kp * p.ncta * 128 + (size_t)(ck * 32) * 128 + m;
+          const float* src = red_src + (size_t)kp * red_stride + (size_t)(ck * 32) * 128;
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] += __ldcg(src + (size_t)j * 128);
         }
@@ -482,7 +473,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CU
           for (int i = 0; i < 8; ++i) c4[i] = __ldg(reinterpret_cast<const float4*>(cvb + ck * 32) + i);
           float v[32];
           __syncwarp();
-          load_acc32(taddr + ck * 32, v);
+          load_acc32(taddr_e + ck * 32, v);
           add_partials(ck, v);
           if (valid) {
             uint4* optr = obase + (size_t)(ck * 4) * oplane;
@@ -575,7 +566,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CU
         // v = accumulator chunk `ck` after emb-silu / residual / clip (everything that precedes the pixel-norm)
         auto compute_v = [&](int ck, float (&v)[32]) {
           __syncwarp();
-          load_acc32(taddr + ck * 32, v);
+          load_acc32(taddr_e + ck * 32, v);
           add_partials(ck, v);
           if (p.epi & TDX_EPI_EMB_SILU) {
 #pragma unroll
@@ -634,7 +625,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CU
             // (2) combine the Cout/ncta CTAs of this M tile through distributed shared memory
             const int par = it & 1;
             if (half == 0) {
-              for (uint32_t r = 0; r < (uint32_t)p.nsplit; ++r) {
+              for (uint32_t r = 0; r < (uint32_t)p.xsplit; ++r) {
                 if (r == my_rank) continue;
                 st_cluster_f32(map_to_cta(smem_u32(&xstat[(par * kMaxSplit + my_rank) * 128 + m]), r), tot);
                 mbar_arrive_cluster(map_to_cta(smem_u32(&x_full[par]), r));
@@ -649,7 +640,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CU
                   }
                 }
               }
-              for (uint32_t r = 0; r < (uint32_t)p.nsplit; ++r)
+              for (uint32_t r = 0; r < (uint32_t)p.xsplit; ++r)
                 if (r != my_rank) tot += xstat[(par * kMaxSplit + r) * 128 + m];
               stot[m] = tot;
             }
@@ -719,7 +710,7 @@ static unsigned long long* g_timeline_ptr = nullptr;   // debug: consecutive lau
 static int g_timeline_idx = 0, g_timeline_cap = 0;
 static int g_dbg_flags = 0;
 
-static int ensure_scratch(float** ws, int** cnt);
+static int ensure_scratch(float** ws);
 
 int igemm_prepare() {
   static bool attr_set = false;
@@ -728,8 +719,7 @@ int igemm_prepare() {
     attr_set = true;
   }
   float* ws;
-  int* cnt;
-  return ensure_scratch(&ws, &cnt);
+  return ensure_scratch(&ws);
 }
 
 static bool needs_norm(const TdxIgemmDesc& d) {
@@ -739,76 +729,107 @@ static bool needs_norm(const TdxIgemmDesc& d) {
   return false;
 }
 
-// Split-K scratch (fp32 partial accumulators + arrival counters), one per device, allocated outside stream capture.
-constexpr size_t kWsBytes = 20u << 20;
-constexpr int kWsCounters = 256;
+// Split-K scratch (fp32 partial accumulators), one per device, allocated outside stream capture.
+constexpr size_t kWsBytes = 24u << 20;
 static float* g_ws[16] = {nullptr};
-static int* g_ws_count[16] = {nullptr};
 
-static int ensure_scratch(float** ws, int** cnt) {
+static int ensure_scratch(float** ws) {
   int dev = 0;
   TDX_CHECK_CUDA(cudaGetDevice(&dev));
   TDX_REQUIRE(dev >= 0 && dev < 16, "igemm: device index %d out of range", dev);
-  if (!g_ws[dev]) {
-    TDX_CHECK_CUDA(cudaMalloc(&g_ws[dev], kWsBytes));
-    TDX_CHECK_CUDA(cudaMalloc(&g_ws_count[dev], kWsCounters * sizeof(int)));
-    TDX_CHECK_CUDA(cudaMemset(g_ws_count[dev], 0, kWsCounters * sizeof(int)));
-  }
+  if (!g_ws[dev]) TDX_CHECK_CUDA(cudaMalloc(&g_ws[dev], kWsBytes));
   *ws = g_ws[dev];
-  *cnt = g_ws_count[dev];
   return TDX_OK;
+}
+
+// How many clusters of `csize` one-CTA-per-SM igemm CTAs the device can hold at once (cached per size).
+static int max_active_clusters(int csize) {
+  static int cache[9] = {0};
+  if (csize <= 1) return sm_count();
+  if (csize > 8) return 0;
+  if (cache[csize]) return cache[csize];
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cudaLaunchAttribute attr[1];
+  cfg.gridDim = dim3((sm_count() / csize) * csize);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = kSmemBudget;
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = csize;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int n = 0;
+  cudaFuncSetAttribute(igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+  if (cudaOccupancyMaxActiveClusters(&n, igemm_kernel, &cfg) != cudaSuccess || n <= 0) {
+    cudaGetLastError();
+    n = (sm_count() * 3 / 4) / csize;   // no GPU to ask (or the query failed): assume some GPCs cannot be filled
+  }
+  cache[csize] = n;
+  return n;
 }
 
 // Choose the output-channel width of a work item (MMA N) and the split-K factor.  Model (cycles), from measurements
 // on B200:
 //   * an SS-mode M=128 K=16 tcgen05.mma costs max(86, N/2) cycles when issued stage by stage (~70 back to back from
 //     smem-resident weights) -- tools/probe/mma_probe.cu, tools/trace_igemm.py;
-//   * L2 -> SM delivers ~2.8 KB/clk chip-wide; per item the A patches (23 KB per 64 input channels) and, unless the
-//     item's whole weight slice fits the B ring ("resident": loaded once per CTA), the weights (N*128 B per stage);
-//   * layers with fewer work items than SMs are a serial MMA chain per CTA: split their K loop over `ks` CTAs that
-//     reduce through an L2-resident fp32 workspace (only when every part fits on the chip at once).
+//   * L2 -> SM delivers ~5 KB/clk chip-wide (tools/sweep_igemm.py) and ~56 B/clk into one SM; per item the A patches (23 KB per 64 input
+//     channels) and, unless the item's whole weight slice fits the B ring ("resident": loaded once per CTA), the
+//     weights (N*128 B per stage);
+//   * layers with fewer work items than SMs are a serial MMA chain per CTA: split their (chunk, tap) stages over the
+//     `ks` CTAs of a cluster, which reduce-scatter fp32 partial sums through L2 (each part then finalises N/ks columns,
+//     so N/ks must be a multiple of the epilogue's 32-column chunk);
+//   * pixel-norm layers exchange statistics inside a cluster, so all nsplit*ks CTAs of an M tile share one (<= 8).
 struct ItemShape { int ncta, resident, sb, ksplit; };
 
-static ItemShape choose_item_shape(int cout, int tiles, int stages, int chunks, int forced_n, bool allow_ksplit,
-                                   bool norm_cluster = false) {
+static ItemShape choose_item_shape(int cout, int tiles, int stages, int chunks, int forced_n, bool norm) {
   if (!forced_n && getenv("TDX_IGEMM_N")) forced_n = atoi(getenv("TDX_IGEMM_N"));
   if (forced_n && (forced_n > cout || cout % forced_n)) forced_n = 0;
-  int forced_k = getenv("TDX_IGEMM_KSPLIT") ? atoi(getenv("TDX_IGEMM_KSPLIT")) : 0;
+  const int forced_k = getenv("TDX_IGEMM_KSPLIT") ? atoi(getenv("TDX_IGEMM_KSPLIT")) : 0;
   const int ring_budget = kSmemBudget - kSA * kAStageBytes - kSmemMisc;
   double best = 1e30;
   ItemShape bs = {64, 0, 2, 1};
   for (int n = 64; n <= 256 && n <= cout; n += 64) {
     if (cout % n) continue;
     if (forced_n && n != forced_n) continue;
-    if (norm_cluster && cout / n > kMaxSplit) continue;   // pixel-norm statistics travel inside one cluster
-    const int stage_bytes = n * 128;
     const int nsplit = cout / n;
+    if (norm && nsplit > kMaxSplit) continue;   // pixel-norm statistics travel inside one cluster
+    const int stage_bytes = n * 128;
     const long items = (long)tiles * nsplit;
     for (int ks = 1; ks <= 8; ++ks) {
-      if (ks > 1 && (!allow_ksplit || ks > chunks || items * ks > sm_count())) break;
-      if (forced_k && allow_ksplit && ks != forced_k && forced_k <= chunks && items * forced_k <= sm_count()) continue;
+      const int csize = ks * ((norm && nsplit > 1) ? nsplit : 1);
+      if (ks > 1) {
+        if (n % (32 * ks) || ks > stages || csize > kMaxSplit) continue;
+        if (items * ks > (long)max_active_clusters(csize) * csize) continue;   // one item per CTA, all resident
+        if ((size_t)items * (ks - 1) * n * 512 > kWsBytes) continue;
+        if (forced_k && ks != forced_k) continue;
+      }
       const int my_stages = (stages + ks - 1) / ks;
+      const int my_chunks = (chunks + ks - 1) / ks + (ks > 1 ? 1 : 0);
       const int resident = (ks == 1 && stages * stage_bytes <= ring_budget && stages <= kMaxSB) ? 1 : 0;
       int sb = resident ? stages : ring_budget / stage_bytes;
       if (sb > kMaxSB) sb = kMaxSB;
       if (sb < 2) continue;
-      if (ks > 1 && ((size_t)items * (ks - 1) * n * 512 > kWsBytes || items > kWsCounters)) continue;
       int grid = items * ks < sm_count() ? (int)(items * ks) : sm_count();
       grid -= grid % (nsplit * ks);
       if (grid <= 0) continue;
       const double rounds = (double)((items * ks + grid - 1) / grid);
       const double cyc = n / 2.0 > 86.0 ? n / 2.0 : 86.0;
       const double mma = rounds * my_stages * 4.0 * cyc + 800.0;
-      const double a_bytes = (double)items * chunks * kAStageBytes;
+      const double a_bytes = (double)items * ks * my_chunks * kAStageBytes;
       const double b_bytes = resident ? (double)grid * stages * stage_bytes : (double)items * stages * stage_bytes;
-      const double l2 = (a_bytes + b_bytes) / 2800.0;
-      const double per_sm = ((double)(chunks * kAStageBytes + stages * stage_bytes) / ks) / 56.0;  // one SM's L2 port
-      const double epi = rounds * (n / 32) * 150.0 / 2.0;
-      const double red = ks > 1 ? (ks - 1) * n * 512.0 / 56.0 + 1500.0 : 0.0;
+      const double red_bytes = ks > 1 ? (double)(ks - 1) / ks * n * 512.0 : 0.0;   // written and read per CTA
+      const double l2 = (a_bytes + b_bytes + 2.0 * red_bytes * items * ks) / 5000.0;
+      const double per_sm = (double)(my_chunks * kAStageBytes + my_stages * stage_bytes) / 56.0;  // one SM's L2 port
+      const int epi_chunks = ((n / ks) / 32 + 1) / 2;
+      const double epi = rounds * epi_chunks * 150.0;
+      const double red = ks > 1 ? 2.0 * red_bytes / 56.0 + 2000.0 : 0.0;
       double t = mma;
       if (l2 > t) t = l2;
       if (per_sm > t) t = per_sm;
       t += epi + red;
+      if (forced_k > 1 && ks == 1) t *= 1e6;   // debug override: take the forced split whenever it is valid
       if (t < best) { best = t; bs = {n, resident, sb, ks}; }
     }
   }
@@ -835,23 +856,23 @@ int igemm_launch(const TdxIgemmDesc& d, const CUtensorMap* tms, cudaStream_t str
   p.tiles_x = (d.width + kTileW - 1) / kTileW;
   p.tiles_y = (d.height + kTileH - 1) / kTileH;
   const int tiles = p.tiles_x * p.tiles_y * d.n_img;
-  const bool norm_split = needs_norm(d);
-  ItemShape shp = choose_item_shape(d.c_out, tiles, p.stages_per_item, chunks, d.n_per_item, !norm_split, norm_split);
-  if (norm_split && d.c_out / shp.ncta == 1) shp = choose_item_shape(d.c_out, tiles, p.stages_per_item, chunks, shp.ncta, true);
+  const bool norm = needs_norm(d);
+  const ItemShape shp = choose_item_shape(d.c_out, tiles, p.stages_per_item, chunks, d.n_per_item, norm);
   p.ncta = shp.ncta;
   p.resident = shp.resident;
   p.SB = shp.sb;
   p.ksplit = shp.ksplit;
-  p.chunks_total = chunks;
   p.nsplit = d.c_out / p.ncta;
   p.b_stage_bytes = p.ncta * 128;
   p.num_items = tiles * p.nsplit * p.ksplit;
   if (p.ksplit > 1) {
-    int rc_ws = ensure_scratch(&p.ws, &p.ws_count);
+    int rc_ws = ensure_scratch(&p.ws);
     if (rc_ws != TDX_OK) return rc_ws;
   }
   p.epi = d.epi_flags;
-  p.cluster_stats = (needs_norm(d) && p.nsplit > 1) ? 1 : 0;
+  p.cluster_stats = (norm && p.nsplit * p.ksplit > 1) ? 1 : 0;
+  p.xsplit = p.cluster_stats ? p.nsplit * p.ksplit : 1;
+  const int cluster = p.cluster_stats ? p.xsplit : p.ksplit;
   p.cvec = d.cvec;
   p.resid = reinterpret_cast<const uint4*>(d.resid);
   p.resid_spatial = d.resid_spatial;
@@ -875,9 +896,9 @@ int igemm_launch(const TdxIgemmDesc& d, const CUtensorMap* tms, cudaStream_t str
   cudaLaunchConfig_t cfg;
   cudaLaunchAttribute attr[2];
   fill_launch_config(&cfg, attr, dim3(grid), dim3(kThreads), smem < 120 * 1024 ? 120 * 1024 : smem, stream);
-  if (p.cluster_stats) {
+  if (cluster > 1) {
     attr[cfg.numAttrs].id = cudaLaunchAttributeClusterDimension;
-    attr[cfg.numAttrs].val.clusterDim.x = p.nsplit;
+    attr[cfg.numAttrs].val.clusterDim.x = cluster;
     attr[cfg.numAttrs].val.clusterDim.y = 1;
     attr[cfg.numAttrs].val.clusterDim.z = 1;
     cfg.attrs = attr;
@@ -947,7 +968,7 @@ extern "C" int tdx_igemm_choose_n(int32_t c_out, int32_t n_img, int32_t height, 
   }
   const int tiles = ((width + tdx::kTileW - 1) / tdx::kTileW) * ((height + tdx::kTileH - 1) / tdx::kTileH) * n_img;
   // conservative: assume the launch may need cluster-wide pixel-norm statistics (slices per tile <= cluster limit)
-  return tdx::choose_item_shape(c_out, tiles, stages, chunks, 0, true, true).ncta;
+  return tdx::choose_item_shape(c_out, tiles, stages, chunks, 0, true).ncta;
 }
 
 // Debug: the (n_per_item, ksplit, resident, ring depth) the launch heuristics pick for a shape.
@@ -960,8 +981,7 @@ extern "C" void tdx_debug_igemm_plan(int32_t c_out, int32_t n_img, int32_t heigh
     chunks += a_channels[s] / 64;
   }
   const int tiles = ((width + tdx::kTileW - 1) / tdx::kTileW) * ((height + tdx::kTileH - 1) / tdx::kTileH) * n_img;
-  tdx::ItemShape shp = tdx::choose_item_shape(c_out, tiles, stages, chunks, n_per_item, !needs_norm, needs_norm != 0);
-  if (needs_norm && c_out / shp.ncta == 1) shp = tdx::choose_item_shape(c_out, tiles, stages, chunks, shp.ncta, true);
+  tdx::ItemShape shp = tdx::choose_item_shape(c_out, tiles, stages, chunks, n_per_item, needs_norm != 0);
   out4[0] = shp.ncta; out4[1] = shp.ksplit; out4[2] = shp.resident; out4[3] = shp.sb;
 }
 
