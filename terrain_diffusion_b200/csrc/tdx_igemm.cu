@@ -42,11 +42,33 @@ constexpr int kAStageBytes = 8 * kKcBytes;        // 64 channels: 23040 B
 constexpr int kSA = 3;                            // A ring depth
 constexpr int kMaxSB = 18;                        // B ring depth (max; also the largest resident weight set)
 constexpr int kAccCols = 256;                     // TMEM columns per accumulator buffer (2 buffers)
-constexpr int kEpiWarps = 8;
+#ifndef TDX_EPI_WQ
+#define TDX_EPI_WQ 2
+#endif
+#ifndef TDX_EPI_CHUNK
+#define TDX_EPI_CHUNK 32
+#endif
+constexpr int kWQ = TDX_EPI_WQ;                   // epilogue warps per TMEM lane quadrant (2 or 4)
+constexpr int kEpiWarps = 4 * kWQ;
+constexpr int kChunk = TDX_EPI_CHUNK;             // accumulator columns an epilogue warp handles at a time (16 or 32)
+constexpr int kGroups = kChunk / 8;               // 8-channel groups (one uint4 of bf16) per chunk
 constexpr int kThreads = 128 + 32 * kEpiWarps;
 constexpr int kMaxSplit = 8;                      // max CTAs (cluster size) sharing one M tile's pixel-norm statistics
-constexpr int kSmemMisc = 12288;                  // barriers, TMEM slot, pixel-norm statistics
+constexpr int kSmemMisc = 14336;                  // barriers, TMEM slot, pixel-norm statistics
 constexpr int kSmemBudget = 227 * 1024;
+
+// Division by a launch constant with a host-made reciprocal: exact while n * d < 2^32 (all uses divide blockIdx.x-sized
+// numbers); keeps runtime integer divisions (~150 cycles each) off the launch's critical path.
+struct FastDiv {
+  uint32_t d, magic;
+};
+static FastDiv make_fastdiv(int d) {
+  FastDiv f;
+  f.d = (uint32_t)d;
+  f.magic = d <= 1 ? 0u : (uint32_t)(0xFFFFFFFFull / (uint32_t)d + 1ull);
+  return f;
+}
+__device__ __forceinline__ uint32_t fdiv(uint32_t n, const FastDiv& f) { return f.d == 1 ? n : __umulhi(n, f.magic); }
 
 struct IgemmParams {
   int nseg;
@@ -54,6 +76,7 @@ struct IgemmParams {
   int seg_taps[3];
   const __nv_bfloat16* B;
   int cout, nsplit;
+  float inv_cout;
   int ncta;                   // output channels per work item = MMA N (64, 128, 192 or 256); cout = ncta * nsplit
   int SB;                     // B ring depth
   int b_stage_bytes;          // ncta * 128
@@ -61,6 +84,8 @@ struct IgemmParams {
   int ksplit;                 // split-K: the (chunk, tap) stages of a work item are shared by the ksplit CTAs of a cluster
   float* ws;                  // split-K fp32 partial sums [group][dst part][ksplit-1 sources][ncta/ksplit cols][128 pixels]
   int H, W, nimg, tiles_x, tiles_y, num_items;
+  FastDiv fd_ks, fd_nsplit, fd_per, fd_tx, fd_ty;   // ksplit, nsplit, nsplit*ksplit, tiles_x, tiles_y
+  int dtx, dty, dimg;                               // the per-iteration tile step gridDim.x / (nsplit*ksplit), decomposed
   int stages_per_item;
   int epi;
   int cluster_stats;          // pixel-norm statistics are exchanged across the xsplit CTAs of a cluster
@@ -75,12 +100,7 @@ struct IgemmParams {
   unsigned long long* trace;  // debug: per-item phase timestamps of CTA 0 (tools/trace_igemm.py), normally null
 };
 
-// K is walked in "stages" (one tap of one 64-channel chunk, in packed-weight order); [s0, s1) = this CTA's share.
-__device__ __forceinline__ void stage_range(const IgemmParams& p, int item, int& s0, int& s1) {
-  const int k = item % p.ksplit;
-  s0 = (p.stages_per_item * k) / p.ksplit;
-  s1 = (p.stages_per_item * (k + 1)) / p.ksplit;
-}
+// K is walked in "stages" (one tap of one 64-channel chunk, in packed-weight order).
 // flat stage index -> (segment, chunk in segment, tap, taps of that segment)
 __device__ __forceinline__ void stage_locate(const IgemmParams& p, int s, int& seg, int& ch, int& tap, int& taps) {
   int base = 0;
@@ -90,7 +110,7 @@ __device__ __forceinline__ void stage_locate(const IgemmParams& p, int s, int& s
     if (s < base + n || seg == p.nseg - 1) break;
     base += n;
   }
-  ch = (s - base) / taps;
+  ch = taps == 9 ? (s - base) / 9 : (s - base);
   tap = (s - base) - ch * taps;
 }
 
@@ -99,17 +119,42 @@ __device__ __forceinline__ void stage_locate(const IgemmParams& p, int s, int& s
     if (p.trace && blockIdx.x == 0 && (it) < 16) p.trace[(it) * 8 + (slot)] = clock64();     \
   } while (0)
 
-// item = ((tile * nsplit) + split) * ksplit + kpart
-__device__ __forceinline__ void decode_item(const IgemmParams& p, int item, int& split, int& img, int& Y0, int& X0) {
-  const int rest = item / p.ksplit;
-  split = rest % p.nsplit;
-  int tile = rest / p.nsplit;
-  int tx = tile % p.tiles_x;
-  int t = tile / p.tiles_x;
-  int ty = t % p.tiles_y;
-  img = t / p.tiles_y;
-  Y0 = ty * kTileH;
-  X0 = tx * kTileW;
+// item = ((tile * nsplit) + split) * ksplit + kpart.  A CTA's items are blockIdx.x, blockIdx.x + gridDim.x, ...;
+// gridDim.x is a multiple of nsplit * ksplit, so the channel slice and the K part are fixed per CTA and only the M tile
+// advances -- by a constant step, which is tracked here without per-item divisions.
+struct TileWalk {
+  int tx, ty, img;      // current M tile
+  int dtx, dty, dimg;   // the tile step, decomposed (dtx < tiles_x, dty < tiles_y)
+  int split, kpart;
+  __device__ __forceinline__ void init(const IgemmParams& p) {
+    const uint32_t b = blockIdx.x;
+    const uint32_t bk = fdiv(b, p.fd_ks);
+    kpart = (int)(b - bk * p.fd_ks.d);
+    split = (int)(bk - fdiv(bk, p.fd_nsplit) * p.fd_nsplit.d);
+    const uint32_t t = fdiv(b, p.fd_per);
+    const uint32_t t1 = fdiv(t, p.fd_tx);
+    tx = (int)(t - t1 * p.fd_tx.d);
+    const uint32_t t2 = fdiv(t1, p.fd_ty);
+    ty = (int)(t1 - t2 * p.fd_ty.d);
+    img = (int)t2;
+    dtx = p.dtx;
+    dty = p.dty;
+    dimg = p.dimg;
+  }
+  __device__ __forceinline__ void next(const IgemmParams& p) {
+    tx += dtx;
+    int c = tx >= p.tiles_x ? 1 : 0;
+    tx -= c ? p.tiles_x : 0;
+    ty += dty + c;
+    c = ty >= p.tiles_y ? 1 : 0;
+    ty -= c ? p.tiles_y : 0;
+    img += dimg + c;
+  }
+};
+// this CTA's share [s0, s1) of an item's K stages (constant per CTA)
+__device__ __forceinline__ void stage_range(const IgemmParams& p, int kpart, int& s0, int& s1) {
+  s0 = (int)fdiv((uint32_t)(p.stages_per_item * kpart), p.fd_ks);
+  s1 = (int)fdiv((uint32_t)(p.stages_per_item * (kpart + 1)), p.fd_ks);
 }
 
 // ---------------------------------------------------------------------------------------------- cluster helpers
@@ -147,39 +192,61 @@ __device__ __forceinline__ void cluster_sync_all() {
 }
 
 // ---------------------------------------------------------------------------------------------- epilogue helpers
-struct OutCtx {
-  uint4* ptr;      // pixel address of this item's first channel group
-  size_t plane;    // uint4 stride between channel groups
-  int Wo;          // output row pitch (pixels)
-  int kind, spatial;
-  float hs, hsk;   // 0.5*scale, 0.5*scale/0.596 for the silu kinds
-  bool active;
-};
-
-__device__ __forceinline__ void store_group(const OutCtx& o, int group, const float* v, float hs, float hsk) {
-  float w[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) w[i] = (o.kind == TDX_OUT_RAW) ? v[i] : mp_silu_scaled(v[i], hs, hsk);
-  uint4 u;
-  u.x = pack_bf16x2(w[0], w[1]);
-  u.y = pack_bf16x2(w[2], w[3]);
-  u.z = pack_bf16x2(w[4], w[5]);
-  u.w = pack_bf16x2(w[6], w[7]);
-  uint4* dst = o.ptr + (size_t)group * o.plane;
-  dst[0] = u;
-  if (o.spatial == TDX_SP_UP2) {
-    dst[1] = u;
-    dst[o.Wo] = u;
-    dst[o.Wo + 1] = u;
-  }
-}
-
-__device__ __forceinline__ void load_acc32(uint32_t taddr, float (&v)[32]) {
-  uint32_t r[32];
-  tmem_ld32(taddr, r);
+__device__ __forceinline__ void load_acc(uint32_t taddr, float (&v)[kChunk]) {
+  uint32_t r[kChunk];
+  if constexpr (kChunk == 32) tmem_ld32(taddr, reinterpret_cast<uint32_t(&)[32]>(r));
+  else tmem_ld16(taddr, reinterpret_cast<uint32_t(&)[16]>(r));
   tmem_ld_wait();
 #pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+  for (int i = 0; i < kChunk; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// 1 / (eps + sqrt(mean square)) with the two MUFU approximations (relative error ~2^-22: invisible after bf16 rounding)
+__device__ __forceinline__ float inv_rms(float sumsq, float inv_n) {
+  float s;
+  asm("sqrt.approx.f32 %0, %1;" : "=f"(s) : "f"(sumsq * inv_n));
+  return __fdividef(1.0f, 1e-4f + s);
+}
+
+// One output of one chunk: kChunk channels of this thread's pixel -> bf16, optionally through mp_silu, one uint4 per
+// 8-channel group (plane stride `plane`), replicated 2x2 for nearest-neighbour upsampling outputs.
+__device__ __forceinline__ void store_chunk(uint4* dst, uint32_t plane, int Wo, int kind, int spatial, bool active,
+                                            const float (&v)[kChunk], float hs, float hsk) {
+  uint4 u[kGroups];
+  if (kind == TDX_OUT_RAW) {
+#pragma unroll
+    for (int g = 0; g < kGroups; ++g) {
+      u[g].x = pack_bf16x2(v[g * 8 + 0], v[g * 8 + 1]);
+      u[g].y = pack_bf16x2(v[g * 8 + 2], v[g * 8 + 3]);
+      u[g].z = pack_bf16x2(v[g * 8 + 4], v[g * 8 + 5]);
+      u[g].w = pack_bf16x2(v[g * 8 + 6], v[g * 8 + 7]);
+    }
+  } else {
+#pragma unroll
+    for (int g = 0; g < kGroups; ++g) {
+      float w[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) w[i] = mp_silu_scaled(v[g * 8 + i], hs, hsk);
+      u[g].x = pack_bf16x2(w[0], w[1]);
+      u[g].y = pack_bf16x2(w[2], w[3]);
+      u[g].z = pack_bf16x2(w[4], w[5]);
+      u[g].w = pack_bf16x2(w[6], w[7]);
+    }
+  }
+  if (!active) return;
+  if (spatial == TDX_SP_UP2) {
+#pragma unroll
+    for (int g = 0; g < kGroups; ++g) {
+      uint4* d = dst + (size_t)g * plane;
+      d[0] = u[g];
+      d[1] = u[g];
+      d[Wo] = u[g];
+      d[Wo + 1] = u[g];
+    }
+  } else {
+#pragma unroll
+    for (int g = 0; g < kGroups; ++g) dst[(size_t)g * plane] = u[g];
+  }
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -197,8 +264,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CU
   uint64_t* t_empty = t_full + 2;
   uint64_t* x_full = t_empty + 2;                                     // [2] cluster statistics barriers
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(x_full + 2);
-  float* ssq = reinterpret_cast<float*>(bars) + 256;                  // [2 column halves][128 pixels]
-  float* stot = ssq + 256;                                            // [128] per-pixel totals for the second half
+  float* ssq = reinterpret_cast<float*>(bars) + 256;                  // [4 epilogue warps of a pixel][128 pixels]
+  float* rss = ssq + 512;                                             // same, for the residual's pixel-norm
+  float* stot = rss + 512;                                            // [128] per-pixel totals over the cluster
   float* xstat = stot + 128;                                          // [2 parity][kMaxSplit][128] from peer CTAs
 
   const int warp = threadIdx.x >> 5;   // warp-uniform role id
@@ -250,12 +318,13 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CU
     int sa = 0;
     uint32_t ph = 0;
     int it = 0;
-    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
-      int split, img, Y0, X0;
-      decode_item(p, item, split, img, Y0, X0);
+    TileWalk tw;
+    tw.init(p);
+    int s0, s1;
+    stage_range(p, tw.kpart, s0, s1);
+    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it, tw.next(p)) {
+      const int img = tw.img, Y0 = tw.ty * kTileH, X0 = tw.tx * kTileW;
       if (lane == 0) TDX_TRACE(0, it);
-      int s0, s1;
-      stage_range(p, item, s0, s1);
       for (int s = s0; s < s1;) {
         int seg, ch, tap, taps;
         stage_locate(p, s, seg, ch, tap, taps);
@@ -276,10 +345,12 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CU
     // Weights are constants: no dependency on the previous kernel, so this starts streaming during its tail.
     int sb = 0;
     uint32_t ph = 0;
+    TileWalk tw;
+    tw.init(p);
+    const int split = tw.split;
+    int st0, st1;
+    stage_range(p, tw.kpart, st0, st1);
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
-      const int split = (item / p.ksplit) % p.nsplit;   // constant per CTA: gridDim.x is a multiple of nsplit*ksplit
-      int st0, st1;
-      stage_range(p, item, st0, st1);
       const uint8_t* bsrc = reinterpret_cast<const uint8_t*>(p.B) +
                             ((size_t)split * p.stages_per_item + st0) * p.b_stage_bytes;
       for (int ks = 0; ks < st1 - st0; ++ks) {
@@ -316,6 +387,11 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CU
     int sa = 0, sb = 0;
     uint32_t pha = 0, phb = 0;
     int it = 0;
+    int s0, s1;
+    {
+      const uint32_t bk = fdiv(blockIdx.x, p.fd_ks);
+      stage_range(p, (int)(blockIdx.x - bk * p.fd_ks.d), s0, s1);
+    }
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
       const int acc = it & 1;
       const uint32_t accph = (it >> 1) & 1;
@@ -325,8 +401,6 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CU
       const uint32_t d_tmem = tmem_base + acc * kAccCols;
       const bool steady = p.resident && it > 0;   // weights already in the ring: no per-stage handshakes
       uint32_t accumulate = 0;
-      int s0, s1;
-      stage_range(p, item, s0, s1);
       {
         for (int s = s0; s < s1;) {
           int seg, ch, tap0, taps;
@@ -391,10 +465,11 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CU
     if (p.ksplit > 1) cluster_sync_all();
   } else if (warp >= 4 && !(p.dbg & 8)) {
     // ------------------------------------------------------------------ epilogue (TMEM -> registers -> global)
-    // warp w and w+4 share TMEM lane quadrant (w & 3); the item's 32-column chunks alternate between the two.
+    // Warp w reads TMEM lane quadrant q = w & 3 (pixels q*32 .. q*32+31, one per lane); the kWQ warps of a quadrant
+    // (wq = 0 .. kWQ-1) take the item's kChunk-column chunks round-robin.
     pdl_wait();  // residual / cvec come from earlier kernels; our stores must not race their readers
     const int q = warp & 3;
-    const int half = (warp - 4) >> 2;
+    const int wq = (warp - 4) >> 2;
     const int m = q * 32 + lane;
     const int y = m >> 3, x = m & 7;
     const int C8 = p.cout >> 3;
@@ -404,13 +479,22 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CU
                            p.out[0].spatial == TDX_SP_SAME && p.out[1].kind == TDX_OUT_NONE &&
                            p.out[2].kind == TDX_OUT_NONE;
     const uint32_t my_rank = p.cluster_stats ? cluster_ctarank() : 0;
+    TileWalk tw;
+    tw.init(p);
+    // Per-CTA constants: with split-K (one item per CTA) this part finalises `slice` of the item's columns.
+    const int ks = p.ksplit, kpart = tw.kpart;
+    const int slice = p.ncta / ks, sch = slice / kChunk;
+    const int nchunks_all = p.ncta / kChunk;              // chunks of the whole accumulator tile
+    const int nchunks = sch;                              // chunks this CTA finalises
+    const int col0 = kpart * slice;                       // first accumulator column this CTA finalises
+    const int chbase = tw.split * p.ncta + col0;          // first output channel this CTA writes
+    const uint32_t plane = (uint32_t)(p.H * p.W);         // (all tensor offsets fit 32 bits: igemm_validate)
     int it = 0;
-    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
+    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it, tw.next(p)) {
       const int acc = it & 1;
       const uint32_t accph = (it >> 1) & 1;
-      int split, img, Y0, X0;
-      decode_item(p, item, split, img, Y0, X0);
-      const int Y = Y0 + y, X = X0 + x;
+      const int img = tw.img;
+      const int Y = tw.ty * kTileH + y, X = tw.tx * kTileW + x;
       const bool valid = (Y < p.H) && (X < p.W);
       const uint32_t taddr = tmem_base + acc * kAccCols + ((uint32_t)(q * 32) << 16);
 
@@ -418,144 +502,122 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CU
       // Reduce-scatter through an L2-resident fp32 workspace: every part publishes the column slices the other parts
       // own, the cluster barrier (release/acquire, all warps of all parts take it once) hands them over, and each part
       // finishes the epilogue of its own ncta/ksplit columns.  (Launches with ksplit > 1 have one item per CTA.)
-      int nchunks = p.ncta >> 5;   // 32-column chunks this CTA finalises
-      int col0 = 0;                // first accumulator column this CTA finalises
       const float* red_src = nullptr;
-      int red_stride = 0;
-      if (p.ksplit > 1) {
-        const int ks = p.ksplit, kpart = item % ks, group = item / ks;
-        const int slice = p.ncta / ks, sch = slice >> 5;
-        float* wsg = p.ws + (size_t)group * (ks - 1) * p.ncta * 128;   // [dst part][source slot][slice cols][128]
+      if (ks > 1) {
+        float* wsg = p.ws + (size_t)fdiv((uint32_t)item, p.fd_ks) * (ks - 1) * p.ncta * 128;   // [dst part][source slot][slice cols][128]
         mbar_wait(&t_full[acc], accph, 600 + acc);
         tc_fence_after();
         if (warp == 4 && lane == 0) TDX_TRACE(7, it);
-        for (int ck = half; ck < nchunks; ck += 2) {
+        for (int ck = wq; ck < nchunks_all; ck += kWQ) {
           const int dst = ck / sch;
           if (dst == kpart) continue;
           const int slot = kpart - (kpart > dst ? 1 : 0);
-          float* d = wsg + ((size_t)(dst * (ks - 1) + slot) * slice + (size_t)(ck - dst * sch) * 32) * 128 + m;
-          float v[32];
+          float* d = wsg + ((size_t)(dst * (ks - 1) + slot) * slice + (size_t)(ck - dst * sch) * kChunk) * 128 + m;
+          float v[kChunk];
           __syncwarp();
-          load_acc32(taddr + ck * 32, v);
+          load_acc(taddr + ck * kChunk, v);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) __stcg(d + (size_t)j * 128, v[j]);
+          for (int j = 0; j < kChunk; ++j) __stcg(d + (size_t)j * 128, v[j]);
         }
         cluster_sync_all();
-        nchunks = sch;
-        col0 = kpart * slice;
         red_src = wsg + (size_t)kpart * (ks - 1) * slice * 128 + m;
-        red_stride = slice * 128;
       }
-      const int chbase = split * p.ncta + col0;           // first output channel this CTA writes
       const uint32_t taddr_e = taddr + col0;
       const float* cvb = p.cvec ? p.cvec + (size_t)img * p.cout + chbase : nullptr;
       // adds the other parts' partial sums to this CTA's chunk ck (no-op without split-K)
-      auto add_partials = [&](int ck, float (&v)[32]) {
-        for (int kp = 0; kp < p.ksplit - 1; ++kp) {
-          const float* src = red_src + (size_t)kp * red_stride + (size_t)(ck * 32) * 128;
+      auto add_partials = [&](int ck, float (&v)[kChunk]) {
+        for (int kp = 0; kp < ks - 1; ++kp) {
+          const float* src = red_src + ((size_t)kp * slice + (size_t)(ck * kChunk)) * 128;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] += __ldcg(src + (size_t)j * 128);
+          for (int j = 0; j < kChunk; ++j) v[j] += __ldcg(src + (size_t)j * 128);
         }
+      };
+      // uint4 offset of this thread's pixel in an NC8HW8 tensor of this launch's (scaled) geometry, channel group 0
+      auto pixel_off = [&](int spatial) -> uint32_t {
+        if (spatial == TDX_SP_DOWN2) return ((uint32_t)(img * C8) * (plane >> 2)) + (uint32_t)((Y >> 1) * (p.W >> 1) + (X >> 1));
+        if (spatial == TDX_SP_UP2) return ((uint32_t)(img * C8) * (plane << 2)) + (uint32_t)((Y << 1) * (p.W << 1) + (X << 1));
+        return (uint32_t)(img * C8) * plane + (uint32_t)(Y * p.W + X);
       };
 
       if (fast_res0) {
         // ---------------- res0: v = mp_silu(acc * c) -> one bf16 output (the common case: half of all launches)
-        const size_t oplane = (size_t)p.H * p.W;
-        uint4* obase = reinterpret_cast<uint4*>(p.out[0].ptr) + ((size_t)img * C8 + (chbase >> 3)) * oplane +
-                       (size_t)Y * p.W + X;
+        uint4* obase = reinterpret_cast<uint4*>(p.out[0].ptr) + pixel_off(TDX_SP_SAME) + (size_t)(chbase >> 3) * plane;
         if (warp == 4 && lane == 0) TDX_TRACE(4, it);
         mbar_wait(&t_full[acc], accph, 600 + acc);
         tc_fence_after();
         if (warp == 4 && lane == 0) TDX_TRACE(5, it);
-        for (int ck = half; ck < ((p.dbg & 4) ? 0 : nchunks); ck += 2) {
-          float4 c4[8];
+        for (int ck = wq; ck < ((p.dbg & 4) ? 0 : nchunks); ck += kWQ) {
+          float4 c4[kChunk / 4];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) c4[i] = __ldg(reinterpret_cast<const float4*>(cvb + ck * 32) + i);
-          float v[32];
+          for (int i = 0; i < kChunk / 4; ++i) c4[i] = __ldg(reinterpret_cast<const float4*>(cvb + ck * kChunk) + i);
+          float v[kChunk];
           __syncwarp();
-          load_acc32(taddr_e + ck * 32, v);
+          load_acc(taddr_e + ck * kChunk, v);
           add_partials(ck, v);
-          if (valid) {
-            uint4* optr = obase + (size_t)(ck * 4) * oplane;
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              const float4 ca = c4[2 * g], cb = c4[2 * g + 1];
-              float w[8];
-              w[0] = mp_silu_f(v[g * 8 + 0] * ca.x);
-              w[1] = mp_silu_f(v[g * 8 + 1] * ca.y);
-              w[2] = mp_silu_f(v[g * 8 + 2] * ca.z);
-              w[3] = mp_silu_f(v[g * 8 + 3] * ca.w);
-              w[4] = mp_silu_f(v[g * 8 + 4] * cb.x);
-              w[5] = mp_silu_f(v[g * 8 + 5] * cb.y);
-              w[6] = mp_silu_f(v[g * 8 + 6] * cb.z);
-              w[7] = mp_silu_f(v[g * 8 + 7] * cb.w);
-              uint4 u;
-              u.x = pack_bf16x2(w[0], w[1]);
-              u.y = pack_bf16x2(w[2], w[3]);
-              u.z = pack_bf16x2(w[4], w[5]);
-              u.w = pack_bf16x2(w[6], w[7]);
-              optr[(size_t)g * oplane] = u;
-            }
+          for (int i = 0; i < kChunk / 4; ++i) {
+            v[4 * i + 0] *= c4[i].x;
+            v[4 * i + 1] *= c4[i].y;
+            v[4 * i + 2] *= c4[i].z;
+            v[4 * i + 3] *= c4[i].w;
           }
+          store_chunk(obase + (size_t)(ck * kGroups) * plane, plane, p.W, TDX_OUT_SILU, TDX_SP_SAME, valid, v, 0.5f,
+                      0.5f / 0.596f);
         }
       } else {
         // ---------------- general: residual mp_sum (+pixel-norm of the residual), clip, pixel-norm, up to 3 outputs
         const uint4* rbase = nullptr;
-        size_t rplane = 0;
+        uint32_t rplane = plane;
         float rscale = p.resid_scale;
-        if ((p.epi & TDX_EPI_RESID) && valid) {
-          int Hr = p.H, Wr = p.W, Yr = Y, Xr = X;
-          if (p.resid_spatial == TDX_SP_UP2) { Hr = p.H >> 1; Wr = p.W >> 1; Yr = Y >> 1; Xr = X >> 1; }
-          else if (p.resid_spatial == TDX_SP_DOWN2) { Hr = p.H << 1; Wr = p.W << 1; Yr = Y << 1; Xr = X << 1; }
-          rplane = (size_t)Hr * Wr;
-          rbase = p.resid + ((size_t)img * C8) * rplane + (size_t)Yr * Wr + Xr;
-          if (p.resid_pnorm) {
-            // the residual's pixel-norm runs over ALL Cout channels (every item reads them; L2-resident);
-            // 8 independent 16-byte loads in flight per step (C8 is a multiple of 8)
-            float ss = 0.f;
-            for (int g0 = 0; g0 < C8; g0 += 8) {
-              uint4 u[8];
-#pragma unroll
-              for (int g = 0; g < 8; ++g) u[g] = __ldg(rbase + (size_t)(g0 + g) * rplane);
-#pragma unroll
-              for (int g = 0; g < 8; ++g) {
-                float a, b;
-                unpack_bf16x2(u[g].x, a, b); ss = fmaf(a, a, fmaf(b, b, ss));
-                unpack_bf16x2(u[g].y, a, b); ss = fmaf(a, a, fmaf(b, b, ss));
-                unpack_bf16x2(u[g].z, a, b); ss = fmaf(a, a, fmaf(b, b, ss));
-                unpack_bf16x2(u[g].w, a, b); ss = fmaf(a, a, fmaf(b, b, ss));
-              }
-            }
-            rscale = p.resid_scale / (1e-4f + sqrtf(ss / (float)p.cout));
-          }
+        if (p.epi & TDX_EPI_RESID) {
+          rplane = p.resid_spatial == TDX_SP_UP2 ? (plane >> 2) : (p.resid_spatial == TDX_SP_DOWN2 ? (plane << 2) : plane);
+          // (a residual "UP2" is read at half resolution, "DOWN2" at double resolution: the inverse of an output's)
+          const int rsp = p.resid_spatial == TDX_SP_UP2 ? TDX_SP_DOWN2 : (p.resid_spatial == TDX_SP_DOWN2 ? TDX_SP_UP2 : TDX_SP_SAME);
+          rbase = p.resid + pixel_off(rsp);
         }
         // prefetch the residual values of this warp's first chunk while the MMAs are still running
-        uint4 rpre[4] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
-        if ((p.epi & TDX_EPI_RESID) && valid && half < nchunks) {
-          const uint4* rptr = rbase + (size_t)((chbase >> 3) + half * 4) * rplane;
+        uint4 rpre[kGroups];
 #pragma unroll
-          for (int g = 0; g < 4; ++g) rpre[g] = __ldg(rptr + (size_t)g * rplane);
+        for (int g = 0; g < kGroups; ++g) rpre[g] = make_uint4(0, 0, 0, 0);
+        if ((p.epi & TDX_EPI_RESID) && valid && wq < nchunks) {
+          const uint4* rptr = rbase + (size_t)((chbase >> 3) + wq * kGroups) * rplane;
+#pragma unroll
+          for (int g = 0; g < kGroups; ++g) rpre[g] = __ldg(rptr + (size_t)g * rplane);
         }
-        OutCtx oc[3];
+        if ((p.epi & TDX_EPI_RESID) && p.resid_pnorm) {
+          // the residual's pixel-norm runs over ALL Cout channels: the kWQ warps of a pixel quadrant each read their
+          // share of the 8-channel planes (C8 is a multiple of 8) and combine through shared memory
+          float ss = 0.f;
+          if (valid) {
+            for (int g0 = wq * 2; g0 < C8; g0 += 2 * kWQ) {
+              const uint4 u0 = __ldg(rbase + (size_t)g0 * rplane), u1 = __ldg(rbase + (size_t)(g0 + 1) * rplane);
+              float a, b;
+              unpack_bf16x2(u0.x, a, b); ss = fmaf(a, a, fmaf(b, b, ss));
+              unpack_bf16x2(u0.y, a, b); ss = fmaf(a, a, fmaf(b, b, ss));
+              unpack_bf16x2(u0.z, a, b); ss = fmaf(a, a, fmaf(b, b, ss));
+              unpack_bf16x2(u0.w, a, b); ss = fmaf(a, a, fmaf(b, b, ss));
+              unpack_bf16x2(u1.x, a, b); ss = fmaf(a, a, fmaf(b, b, ss));
+              unpack_bf16x2(u1.y, a, b); ss = fmaf(a, a, fmaf(b, b, ss));
+              unpack_bf16x2(u1.z, a, b); ss = fmaf(a, a, fmaf(b, b, ss));
+              unpack_bf16x2(u1.w, a, b); ss = fmaf(a, a, fmaf(b, b, ss));
+            }
+          }
+          rss[wq * 128 + m] = ss;
+          named_bar_sync(9 + q, 32 * kWQ);
+          ss = 0.f;
+#pragma unroll
+          for (int w = 0; w < kWQ; ++w) ss += rss[w * 128 + m];
+          rscale = p.resid_scale * inv_rms(ss, p.inv_cout);
+        }
+        // this thread's pixel in each output (inactive: out of the image, or an odd pixel of a 2x-downsampled output)
+        uint4* optr[3];
+        bool oact[3];
 #pragma unroll
         for (int o = 0; o < 3; ++o) {
-          const TdxOutSpec& os = p.out[o];
-          oc[o].kind = os.kind;
-          oc[o].spatial = os.spatial;
-          oc[o].active = (os.kind != TDX_OUT_NONE) && valid;
-          int Ho = p.H, Wo = p.W, Yo = Y, Xo = X;
-          if (os.spatial == TDX_SP_DOWN2) {
-            if ((Y | X) & 1) oc[o].active = false;
-            Ho >>= 1; Wo >>= 1; Yo >>= 1; Xo >>= 1;
-          } else if (os.spatial == TDX_SP_UP2) {
-            Ho <<= 1; Wo <<= 1; Yo <<= 1; Xo <<= 1;
-          }
-          oc[o].plane = (size_t)Ho * Wo;
-          oc[o].Wo = Wo;
-          oc[o].ptr = reinterpret_cast<uint4*>(os.ptr) + ((size_t)img * C8 + (chbase >> 3)) * oc[o].plane +
-                      (size_t)Yo * Wo + Xo;
-          oc[o].hs = 0.5f * os.scale;
-          oc[o].hsk = 0.5f * os.scale * (1.0f / 0.596f);
+          const int sp = p.out[o].spatial;
+          oact[o] = (p.out[o].kind != TDX_OUT_NONE) && valid && !(sp == TDX_SP_DOWN2 && ((Y | X) & 1));
+          const uint32_t oplane = sp == TDX_SP_DOWN2 ? (plane >> 2) : (sp == TDX_SP_UP2 ? (plane << 2) : plane);
+          optr[o] = reinterpret_cast<uint4*>(p.out[o].ptr) + pixel_off(sp) + (size_t)(chbase >> 3) * oplane;
         }
 
         if (warp == 4 && lane == 0) TDX_TRACE(4, it);
@@ -564,14 +626,14 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CU
         if (warp == 4 && lane == 0) TDX_TRACE(5, it);
 
         // v = accumulator chunk `ck` after emb-silu / residual / clip (everything that precedes the pixel-norm)
-        auto compute_v = [&](int ck, float (&v)[32]) {
+        auto compute_v = [&](int ck, float (&v)[kChunk]) {
           __syncwarp();
-          load_acc32(taddr_e + ck * 32, v);
+          load_acc(taddr_e + ck * kChunk, v);
           add_partials(ck, v);
           if (p.epi & TDX_EPI_EMB_SILU) {
 #pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              float4 c4 = __ldg(reinterpret_cast<const float4*>(cvb + ck * 32 + i));
+            for (int i = 0; i < kChunk; i += 4) {
+              float4 c4 = __ldg(reinterpret_cast<const float4*>(cvb + ck * kChunk + i));
               v[i + 0] = mp_silu_f(v[i + 0] * c4.x);
               v[i + 1] = mp_silu_f(v[i + 1] * c4.y);
               v[i + 2] = mp_silu_f(v[i + 2] * c4.z);
@@ -579,10 +641,10 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CU
             }
           }
           if (p.epi & TDX_EPI_RESID) {
-            const uint4* rptr = rbase + (size_t)((chbase >> 3) + ck * 4) * rplane;
+            const uint4* rptr = rbase + (size_t)((chbase >> 3) + ck * kGroups) * rplane;
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              uint4 u = (ck == half) ? rpre[g] : (valid ? __ldg(rptr + (size_t)g * rplane) : make_uint4(0, 0, 0, 0));
+            for (int g = 0; g < kGroups; ++g) {
+              uint4 u = (ck == wq) ? rpre[g] : (valid ? __ldg(rptr + (size_t)g * rplane) : make_uint4(0, 0, 0, 0));
               float rr[8];
               unpack_bf16x2(u.x, rr[0], rr[1]);
               unpack_bf16x2(u.y, rr[2], rr[3]);
@@ -594,37 +656,38 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CU
           }
           if (p.clip > 0.f) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = fminf(fmaxf(v[i], -p.clip), p.clip);
+            for (int i = 0; i < kChunk; ++i) v[i] = fminf(fmaxf(v[i], -p.clip), p.clip);
           }
         };
-        auto emit_v = [&](int ck, float (&v)[32], float inv) {
+        auto emit_v = [&](int ck, float (&v)[kChunk], float inv) {
           if (p.epi & TDX_EPI_PNORM) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] *= inv;
+            for (int i = 0; i < kChunk; ++i) v[i] *= inv;
           }
 #pragma unroll
           for (int o = 0; o < 3; ++o) {
-            if (!oc[o].active) continue;
-            float hs = oc[o].hs, hsk = oc[o].hsk;
-            if (oc[o].kind == TDX_OUT_PNORM_SILU) {
-              const float sc = (p.epi & TDX_EPI_PNORM) ? 1.0f : inv;
-              hs = 0.5f * sc;
-              hsk = 0.5f * sc * (1.0f / 0.596f);
-            }
-#pragma unroll
-            for (int g = 0; g < 4; ++g) store_group(oc[o], ck * 4 + g, v + g * 8, hs, hsk);
+            const int kind = p.out[o].kind, sp = p.out[o].spatial;
+            if (kind == TDX_OUT_NONE) continue;
+            float hs = 0.5f * p.out[o].scale;
+            if (kind == TDX_OUT_PNORM_SILU) hs = (p.epi & TDX_EPI_PNORM) ? 0.5f : 0.5f * inv;
+            const uint32_t oplane = sp == TDX_SP_DOWN2 ? (plane >> 2) : (sp == TDX_SP_UP2 ? (plane << 2) : plane);
+            const int Wo = sp == TDX_SP_DOWN2 ? (p.W >> 1) : (sp == TDX_SP_UP2 ? (p.W << 1) : p.W);
+            store_chunk(optr[o] + (size_t)(ck * kGroups) * oplane, oplane, Wo, kind, sp, oact[o], v, hs,
+                        hs * (1.0f / 0.596f));
           }
         };
         // per-pixel sum of squares over ALL Cout channels -> 1 / (eps + rms)
         auto finish_norm = [&](float sumsq) -> float {
-          // (1) combine the two warps that own the same pixels (named barrier per lane quadrant)
-          ssq[half * 128 + m] = sumsq;
-          named_bar_sync(1 + q, 64);
-          float tot = ssq[m] + ssq[128 + m];
+          // (1) combine the warps that own the same pixels (named barrier per lane quadrant)
+          ssq[wq * 128 + m] = sumsq;
+          named_bar_sync(1 + q, 32 * kWQ);
+          float tot = 0.f;
+#pragma unroll
+          for (int w = 0; w < kWQ; ++w) tot += ssq[w * 128 + m];
           if (p.cluster_stats) {
-            // (2) combine the Cout/ncta CTAs of this M tile through distributed shared memory
+            // (2) combine the CTAs that hold the other channels of this M tile through distributed shared memory
             const int par = it & 1;
-            if (half == 0) {
+            if (wq == 0) {
               for (uint32_t r = 0; r < (uint32_t)p.xsplit; ++r) {
                 if (r == my_rank) continue;
                 st_cluster_f32(map_to_cta(smem_u32(&xstat[(par * kMaxSplit + my_rank) * 128 + m]), r), tot);
@@ -644,38 +707,38 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CU
                 if (r != my_rank) tot += xstat[(par * kMaxSplit + r) * 128 + m];
               stot[m] = tot;
             }
-            named_bar_sync(5 + q, 64);
+            named_bar_sync(5 + q, 32 * kWQ);
             tot = stot[m];
           }
-          return 1.0f / (1e-4f + sqrtf(tot / (float)p.cout));
+          return inv_rms(tot, p.inv_cout);
         };
 
         if (!(p.dbg & 4)) {
-          float v[32];
+          float v[kChunk];
           if (!need_norm) {
-            for (int ck = half; ck < nchunks; ck += 2) {
+            for (int ck = wq; ck < nchunks; ck += kWQ) {
               compute_v(ck, v);
               emit_v(ck, v, 1.f);
             }
-          } else if (nchunks <= 2) {
-            // one chunk per warp: keep it in registers across the statistics exchange
+          } else if (nchunks <= kWQ) {
+            // at most one chunk per warp: keep it in registers across the statistics exchange
             float sumsq = 0.f;
-            if (half < nchunks) {
-              compute_v(half, v);
+            if (wq < nchunks) {
+              compute_v(wq, v);
 #pragma unroll
-              for (int i = 0; i < 32; ++i) sumsq = fmaf(v[i], v[i], sumsq);
+              for (int i = 0; i < kChunk; ++i) sumsq = fmaf(v[i], v[i], sumsq);
             }
             const float inv = finish_norm(sumsq);
-            if (half < nchunks) emit_v(half, v, inv);
+            if (wq < nchunks) emit_v(wq, v, inv);
           } else {
             float sumsq = 0.f;
-            for (int ck = half; ck < nchunks; ck += 2) {
+            for (int ck = wq; ck < nchunks; ck += kWQ) {
               compute_v(ck, v);
 #pragma unroll
-              for (int i = 0; i < 32; ++i) sumsq = fmaf(v[i], v[i], sumsq);
+              for (int i = 0; i < kChunk; ++i) sumsq = fmaf(v[i], v[i], sumsq);
             }
             const float inv = finish_norm(sumsq);
-            for (int ck = half; ck < nchunks; ck += 2) {
+            for (int ck = wq; ck < nchunks; ck += kWQ) {
               compute_v(ck, v);
               emit_v(ck, v, inv);
             }
@@ -800,7 +863,7 @@ static ItemShape choose_item_shape(int cout, int tiles, int stages, int chunks, 
     for (int ks = 1; ks <= 8; ++ks) {
       const int csize = ks * ((norm && nsplit > 1) ? nsplit : 1);
       if (ks > 1) {
-        if (n % (32 * ks) || ks > stages || csize > kMaxSplit) continue;
+        if (n % (kChunk * ks) || ks > stages || csize > kMaxSplit) continue;
         if (items * ks > (long)max_active_clusters(csize) * csize) continue;   // one item per CTA, all resident
         if ((size_t)items * (ks - 1) * n * 512 > kWsBytes) continue;
         if (forced_k && ks != forced_k) continue;
@@ -822,8 +885,8 @@ static ItemShape choose_item_shape(int cout, int tiles, int stages, int chunks, 
       const double red_bytes = ks > 1 ? (double)(ks - 1) / ks * n * 512.0 : 0.0;   // written and read per CTA
       const double l2 = (a_bytes + b_bytes + 2.0 * red_bytes * items * ks) / 5000.0;
       const double per_sm = (double)(my_chunks * kAStageBytes + my_stages * stage_bytes) / 56.0;  // one SM's L2 port
-      const int epi_chunks = ((n / ks) / 32 + 1) / 2;
-      const double epi = rounds * epi_chunks * 150.0;
+      const int epi_chunks = ((n / ks) / kChunk + 3) / 4;
+      const double epi = rounds * epi_chunks * 100.0;
       const double red = ks > 1 ? 2.0 * red_bytes / 56.0 + 2000.0 : 0.0;
       double t = mma;
       if (l2 > t) t = l2;
@@ -850,6 +913,7 @@ int igemm_launch(const TdxIgemmDesc& d, const CUtensorMap* tms, cudaStream_t str
   }
   p.B = reinterpret_cast<const __nv_bfloat16*>(d.b_packed);
   p.cout = d.c_out;
+  p.inv_cout = 1.0f / (float)d.c_out;
   p.H = d.height;
   p.W = d.width;
   p.nimg = d.n_img;
@@ -889,6 +953,19 @@ int igemm_launch(const TdxIgemmDesc& d, const CUtensorMap* tms, cudaStream_t str
   // grid: one CTA per SM at most, a multiple of nsplit so the slices of an M tile always run side by side
   int grid = p.num_items < sm_count() ? p.num_items : sm_count();
   grid -= grid % (p.nsplit * p.ksplit);
+  {
+    const int per = p.nsplit * p.ksplit;
+    p.fd_ks = make_fastdiv(p.ksplit);
+    p.fd_nsplit = make_fastdiv(p.nsplit);
+    p.fd_per = make_fastdiv(per);
+    p.fd_tx = make_fastdiv(p.tiles_x);
+    p.fd_ty = make_fastdiv(p.tiles_y);
+    int dstep = grid / per;
+    p.dtx = dstep % p.tiles_x;
+    dstep /= p.tiles_x;
+    p.dty = dstep % p.tiles_y;
+    p.dimg = dstep / p.tiles_y;
+  }
   const int smem = kSA * kAStageBytes + p.SB * p.b_stage_bytes + kSmemMisc;
   const CUtensorMap& t0 = tms[0];
   const CUtensorMap& t1 = tms[d.n_seg > 1 ? 1 : 0];
@@ -925,6 +1002,9 @@ int igemm_validate(const TdxIgemmDesc& d) {
   TDX_REQUIRE(d.n_per_item >= 64 && d.n_per_item <= 256 && d.n_per_item % 64 == 0 && d.c_out % d.n_per_item == 0,
               "igemm: n_per_item=%d must be 64/128/192/256 and divide c_out=%d (use tdx_igemm_choose_n)", d.n_per_item,
               d.c_out);
+  TDX_REQUIRE((unsigned long long)d.n_img * (d.c_out / 8) * d.height * d.width * 4ull < (1ull << 32),
+              "igemm: tensor of %d x %d x %d x %d exceeds the 32-bit element offsets of the epilogue", d.n_img, d.c_out,
+              d.height, d.width);
   TDX_REQUIRE(d.n_img >= 1 && d.height >= 8 && d.width >= 8 && d.height % 8 == 0 && d.width % 8 == 0,
               "igemm: bad shape n=%d h=%d w=%d (h, w multiples of 8)", d.n_img, d.height, d.width);
   if (d.epi_flags & TDX_EPI_EMB_SILU) TDX_REQUIRE(d.cvec != nullptr, "igemm: EMB_SILU needs cvec");
