@@ -392,7 +392,74 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CU
       const uint32_t bk = fdiv(blockIdx.x, p.fd_ks);
       stage_range(p, (int)(blockIdx.x - bk * p.fd_ks.d), s0, s1);
     }
+    const bool fastloop = p.resident && p.nseg == 1 && p.seg_taps[0] == 9 && p.ksplit == 1;
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
+      if (fastloop && it > 0) {
+        // ---- Steady state of the persistent single-segment 3x3 case (weights resident, every chunk = 36 MMAs).
+        // The barriers of the NEXT chunk are probed (never blocked on) between the 24th and 25th MMA of the current one,
+        // while the tensor pipe still has queued work; a successful probe removes the wait from the gap between chunks.
+        const int nchunk = p.seg_chunks[0];
+        bool a_ok = false, te_ok = false;
+        for (;;) {
+          const int acc = it & 1;
+          const uint32_t d_tmem = tmem_base + acc * kAccCols;
+          const int next_item = item + (int)gridDim.x;
+          if (!te_ok) mbar_wait(&t_empty[acc], ((it >> 1) & 1) ^ 1, 300 + acc);
+          if (lane == 0) TDX_TRACE(1, it);
+          for (int c = 0; c < nchunk; ++c) {
+            if (!a_ok) mbar_wait(&a_full[sa], pha, 400 + sa);
+            tc_fence_after();
+            if (lane == 0 && c == 0) TDX_TRACE(2, it);
+            const uint32_t a16 = a_ring16 + sa * (kAStageBytes >> 4);
+            const uint32_t b16 = b_ring16 + c * 9 * b_stage16;
+            if (elect_one()) {
+#pragma unroll
+              for (int tap = 0; tap < 6; ++tap) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const uint64_t adesc = a_hi | (uint64_t)(a16 + (tap / 3) * kPatchW + (tap % 3) + j * a_kstep16);
+                  const uint64_t bdesc = b_hi | (uint64_t)(b16 + tap * b_stage16 + j * b_kstep16);
+                  umma_bf16(d_tmem, adesc, bdesc, idesc, (c | tap | j) ? 1u : 0u);
+                }
+              }
+            }
+            __syncwarp();
+            const bool last_c = (c == nchunk - 1);
+            int sa_n = sa + 1;
+            uint32_t pha_n = pha;
+            if (sa_n == kSA) { sa_n = 0; pha_n ^= 1; }
+            a_ok = false;
+            if (!last_c || next_item < p.num_items) {
+              a_ok = mbar_test_wait(&a_full[sa_n], pha_n);
+              if (last_c) {
+                const int itn = it + 1;
+                te_ok = mbar_test_wait(&t_empty[itn & 1], ((itn >> 1) & 1) ^ 1);
+              }
+            }
+            if (elect_one()) {
+#pragma unroll
+              for (int tap = 6; tap < 9; ++tap) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const uint64_t adesc = a_hi | (uint64_t)(a16 + (tap / 3) * kPatchW + (tap % 3) + j * a_kstep16);
+                  const uint64_t bdesc = b_hi | (uint64_t)(b16 + tap * b_stage16 + j * b_kstep16);
+                  umma_bf16(d_tmem, adesc, bdesc, idesc, 1u);
+                }
+              }
+              umma_commit(&a_empty[sa]);
+              if (last_c) umma_commit(&t_full[acc]);
+            }
+            __syncwarp();
+            sa = sa_n;
+            pha = pha_n;
+          }
+          if (lane == 0) TDX_TRACE(3, it);
+          item = next_item;
+          ++it;
+          if (item >= p.num_items) break;
+        }
+        break;
+      }
       const int acc = it & 1;
       const uint32_t accph = (it >> 1) & 1;
       mbar_wait(&t_empty[acc], accph ^ 1, 300 + acc);
@@ -475,9 +542,6 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CU
     const int C8 = p.cout >> 3;
     const bool need_norm = (p.epi & TDX_EPI_PNORM) || p.out[0].kind == TDX_OUT_PNORM_SILU ||
                            p.out[1].kind == TDX_OUT_PNORM_SILU || p.out[2].kind == TDX_OUT_PNORM_SILU;
-    const bool fast_res0 = (p.epi == TDX_EPI_EMB_SILU) && p.clip <= 0.f && p.out[0].kind == TDX_OUT_RAW &&
-                           p.out[0].spatial == TDX_SP_SAME && p.out[1].kind == TDX_OUT_NONE &&
-                           p.out[2].kind == TDX_OUT_NONE;
     const uint32_t my_rank = p.cluster_stats ? cluster_ctarank() : 0;
     TileWalk tw;
     tw.init(p);
@@ -489,6 +553,38 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CU
     const int col0 = kpart * slice;                       // first accumulator column this CTA finalises
     const int chbase = tw.split * p.ncta + col0;          // first output channel this CTA writes
     const uint32_t plane = (uint32_t)(p.H * p.W);         // (all tensor offsets fit 32 bits: igemm_validate)
+    // uint4 offset of a pixel in an NC8HW8 tensor of this launch's (scaled) geometry, channel group 0
+    auto pixel_off_at = [&](int spatial, int img_, int Y_, int X_) -> uint32_t {
+      if (spatial == TDX_SP_DOWN2)
+        return ((uint32_t)(img_ * C8) * (plane >> 2)) + (uint32_t)((Y_ >> 1) * (p.W >> 1) + (X_ >> 1));
+      if (spatial == TDX_SP_UP2)
+        return ((uint32_t)(img_ * C8) * (plane << 2)) + (uint32_t)((Y_ << 1) * (p.W << 1) + (X_ << 1));
+      return (uint32_t)(img_ * C8) * plane + (uint32_t)(Y_ * p.W + X_);
+    };
+    // Residual reads.  "UP2" = the residual is at half resolution, "DOWN2" = at double resolution (the inverse of an
+    // output's meaning).  Per item a thread needs its pixel's first-chunk channels (rpre) and, for the residual's
+    // pixel-norm, its share of ALL Cout channels (upre = the first four 8-channel planes of that share).
+    // (Requesting the NEXT item's values from inside the current item's epilogue was tried: the loads queue ahead of
+    // the output stores and the item gets slower, 28.4k -> 30.6k cycles on the 256^2 res1 layer.)
+    const bool has_resid = (p.epi & TDX_EPI_RESID) != 0;
+    const uint32_t rplane = p.resid_spatial == TDX_SP_UP2 ? (plane >> 2) : (p.resid_spatial == TDX_SP_DOWN2 ? (plane << 2) : plane);
+    const int rsp = p.resid_spatial == TDX_SP_UP2 ? TDX_SP_DOWN2 : (p.resid_spatial == TDX_SP_DOWN2 ? TDX_SP_UP2 : TDX_SP_SAME);
+    uint4 upre[4], rpre[kGroups];
+    const uint4* rbase_pre = nullptr;
+    auto resid_fetch = [&](const TileWalk& t) {
+      const int Y_ = t.ty * kTileH + y, X_ = t.tx * kTileW + x;
+      const bool vld = (Y_ < p.H) && (X_ < p.W);
+      rbase_pre = p.resid + pixel_off_at(rsp, t.img, Y_, X_);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int g = wq * 2 + (j >> 1) * 2 * kWQ + (j & 1);
+        upre[j] = (vld && p.resid_pnorm && g < C8) ? __ldg(rbase_pre + (size_t)g * rplane) : make_uint4(0, 0, 0, 0);
+      }
+      const uint4* rptr = rbase_pre + (size_t)((chbase >> 3) + wq * kGroups) * rplane;
+#pragma unroll
+      for (int g = 0; g < kGroups; ++g)
+        rpre[g] = (vld && wq < nchunks) ? __ldg(rptr + (size_t)g * rplane) : make_uint4(0, 0, 0, 0);
+    };
     int it = 0;
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it, tw.next(p)) {
       const int acc = it & 1;
@@ -533,73 +629,31 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CU
         }
       };
       // uint4 offset of this thread's pixel in an NC8HW8 tensor of this launch's (scaled) geometry, channel group 0
-      auto pixel_off = [&](int spatial) -> uint32_t {
-        if (spatial == TDX_SP_DOWN2) return ((uint32_t)(img * C8) * (plane >> 2)) + (uint32_t)((Y >> 1) * (p.W >> 1) + (X >> 1));
-        if (spatial == TDX_SP_UP2) return ((uint32_t)(img * C8) * (plane << 2)) + (uint32_t)((Y << 1) * (p.W << 1) + (X << 1));
-        return (uint32_t)(img * C8) * plane + (uint32_t)(Y * p.W + X);
-      };
+      auto pixel_off = [&](int spatial) -> uint32_t { return pixel_off_at(spatial, img, Y, X); };
 
-      if (fast_res0) {
-        // ---------------- res0: v = mp_silu(acc * c) -> one bf16 output (the common case: half of all launches)
-        uint4* obase = reinterpret_cast<uint4*>(p.out[0].ptr) + pixel_off(TDX_SP_SAME) + (size_t)(chbase >> 3) * plane;
-        if (warp == 4 && lane == 0) TDX_TRACE(4, it);
-        mbar_wait(&t_full[acc], accph, 600 + acc);
-        tc_fence_after();
-        if (warp == 4 && lane == 0) TDX_TRACE(5, it);
-        for (int ck = wq; ck < ((p.dbg & 4) ? 0 : nchunks); ck += kWQ) {
-          float4 c4[kChunk / 4];
-#pragma unroll
-          for (int i = 0; i < kChunk / 4; ++i) c4[i] = __ldg(reinterpret_cast<const float4*>(cvb + ck * kChunk) + i);
-          float v[kChunk];
-          __syncwarp();
-          load_acc(taddr_e + ck * kChunk, v);
-          add_partials(ck, v);
-#pragma unroll
-          for (int i = 0; i < kChunk / 4; ++i) {
-            v[4 * i + 0] *= c4[i].x;
-            v[4 * i + 1] *= c4[i].y;
-            v[4 * i + 2] *= c4[i].z;
-            v[4 * i + 3] *= c4[i].w;
-          }
-          store_chunk(obase + (size_t)(ck * kGroups) * plane, plane, p.W, TDX_OUT_SILU, TDX_SP_SAME, valid, v, 0.5f,
-                      0.5f / 0.596f);
-        }
-      } else {
+      {
         // ---------------- general: residual mp_sum (+pixel-norm of the residual), clip, pixel-norm, up to 3 outputs
-        const uint4* rbase = nullptr;
-        uint32_t rplane = plane;
         float rscale = p.resid_scale;
-        if (p.epi & TDX_EPI_RESID) {
-          rplane = p.resid_spatial == TDX_SP_UP2 ? (plane >> 2) : (p.resid_spatial == TDX_SP_DOWN2 ? (plane << 2) : plane);
-          // (a residual "UP2" is read at half resolution, "DOWN2" at double resolution: the inverse of an output's)
-          const int rsp = p.resid_spatial == TDX_SP_UP2 ? TDX_SP_DOWN2 : (p.resid_spatial == TDX_SP_DOWN2 ? TDX_SP_UP2 : TDX_SP_SAME);
-          rbase = p.resid + pixel_off(rsp);
-        }
-        // prefetch the residual values of this warp's first chunk while the MMAs are still running
-        uint4 rpre[kGroups];
-#pragma unroll
-        for (int g = 0; g < kGroups; ++g) rpre[g] = make_uint4(0, 0, 0, 0);
-        if ((p.epi & TDX_EPI_RESID) && valid && wq < nchunks) {
-          const uint4* rptr = rbase + (size_t)((chbase >> 3) + wq * kGroups) * rplane;
-#pragma unroll
-          for (int g = 0; g < kGroups; ++g) rpre[g] = __ldg(rptr + (size_t)g * rplane);
-        }
-        if ((p.epi & TDX_EPI_RESID) && p.resid_pnorm) {
+        if (has_resid) resid_fetch(tw);   // issued before the accumulator wait: overlaps the MMAs of this item
+        const uint4* rbase = rbase_pre;
+        if (has_resid && p.resid_pnorm) {
           // the residual's pixel-norm runs over ALL Cout channels: the kWQ warps of a pixel quadrant each read their
           // share of the 8-channel planes (C8 is a multiple of 8) and combine through shared memory
           float ss = 0.f;
+          auto sq8 = [&](const uint4& u) {
+            float a, b;
+            unpack_bf16x2(u.x, a, b); ss = fmaf(a, a, fmaf(b, b, ss));
+            unpack_bf16x2(u.y, a, b); ss = fmaf(a, a, fmaf(b, b, ss));
+            unpack_bf16x2(u.z, a, b); ss = fmaf(a, a, fmaf(b, b, ss));
+            unpack_bf16x2(u.w, a, b); ss = fmaf(a, a, fmaf(b, b, ss));
+          };
+#pragma unroll
+          for (int j = 0; j < 4; ++j) sq8(upre[j]);
           if (valid) {
-            for (int g0 = wq * 2; g0 < C8; g0 += 2 * kWQ) {
+            for (int g0 = wq * 2 + 4 * kWQ; g0 < C8; g0 += 2 * kWQ) {
               const uint4 u0 = __ldg(rbase + (size_t)g0 * rplane), u1 = __ldg(rbase + (size_t)(g0 + 1) * rplane);
-              float a, b;
-              unpack_bf16x2(u0.x, a, b); ss = fmaf(a, a, fmaf(b, b, ss));
-              unpack_bf16x2(u0.y, a, b); ss = fmaf(a, a, fmaf(b, b, ss));
-              unpack_bf16x2(u0.z, a, b); ss = fmaf(a, a, fmaf(b, b, ss));
-              unpack_bf16x2(u0.w, a, b); ss = fmaf(a, a, fmaf(b, b, ss));
-              unpack_bf16x2(u1.x, a, b); ss = fmaf(a, a, fmaf(b, b, ss));
-              unpack_bf16x2(u1.y, a, b); ss = fmaf(a, a, fmaf(b, b, ss));
-              unpack_bf16x2(u1.z, a, b); ss = fmaf(a, a, fmaf(b, b, ss));
-              unpack_bf16x2(u1.w, a, b); ss = fmaf(a, a, fmaf(b, b, ss));
+              sq8(u0);
+              sq8(u1);
             }
           }
           rss[wq * 128 + m] = ss;
@@ -714,34 +768,25 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CU
         };
 
         if (!(p.dbg & 4)) {
+          // One code path for all cases (keeps the kernel small enough for the instruction cache): an optional
+          // statistics pass, then the emitting pass.  When every warp has at most one chunk, it stays in registers
+          // across the statistics exchange instead of being recomputed.
           float v[kChunk];
-          if (!need_norm) {
+          float sumsq = 0.f, inv = 1.f;
+          const bool reuse = need_norm && nchunks <= kWQ;
+#pragma unroll 1
+          for (int pass = need_norm ? 0 : 1; pass < 2; ++pass) {
+#pragma unroll 1
             for (int ck = wq; ck < nchunks; ck += kWQ) {
-              compute_v(ck, v);
-              emit_v(ck, v, 1.f);
-            }
-          } else if (nchunks <= kWQ) {
-            // at most one chunk per warp: keep it in registers across the statistics exchange
-            float sumsq = 0.f;
-            if (wq < nchunks) {
-              compute_v(wq, v);
+              if (pass == 0 || !reuse) compute_v(ck, v);
+              if (pass == 0) {
 #pragma unroll
-              for (int i = 0; i < kChunk; ++i) sumsq = fmaf(v[i], v[i], sumsq);
+                for (int i = 0; i < kChunk; ++i) sumsq = fmaf(v[i], v[i], sumsq);
+              } else {
+                emit_v(ck, v, inv);
+              }
             }
-            const float inv = finish_norm(sumsq);
-            if (wq < nchunks) emit_v(wq, v, inv);
-          } else {
-            float sumsq = 0.f;
-            for (int ck = wq; ck < nchunks; ck += kWQ) {
-              compute_v(ck, v);
-#pragma unroll
-              for (int i = 0; i < kChunk; ++i) sumsq = fmaf(v[i], v[i], sumsq);
-            }
-            const float inv = finish_norm(sumsq);
-            for (int ck = wq; ck < nchunks; ck += kWQ) {
-              compute_v(ck, v);
-              emit_v(ck, v, inv);
-            }
+            if (pass == 0) inv = finish_norm(sumsq);
           }
         }
       }
