@@ -392,80 +392,15 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CU
       const uint32_t bk = fdiv(blockIdx.x, p.fd_ks);
       stage_range(p, (int)(blockIdx.x - bk * p.fd_ks.d), s0, s1);
     }
-    const bool fastloop = p.resident && p.nseg == 1 && p.seg_taps[0] == 9 && p.ksplit == 1;
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
-      if (fastloop && it > 0) {
-        // ---- Steady state of the persistent single-segment 3x3 case (weights resident, every chunk = 36 MMAs).
-        // The barriers of the NEXT chunk are probed (never blocked on) between the 24th and 25th MMA of the current one,
-        // while the tensor pipe still has queued work; a successful probe removes the wait from the gap between chunks.
-        const int nchunk = p.seg_chunks[0];
-        bool a_ok = false, te_ok = false;
-        for (;;) {
-          const int acc = it & 1;
-          const uint32_t d_tmem = tmem_base + acc * kAccCols;
-          const int next_item = item + (int)gridDim.x;
-          if (!te_ok) mbar_wait(&t_empty[acc], ((it >> 1) & 1) ^ 1, 300 + acc);
-          if (lane == 0) TDX_TRACE(1, it);
-          for (int c = 0; c < nchunk; ++c) {
-            if (!a_ok) mbar_wait(&a_full[sa], pha, 400 + sa);
-            tc_fence_after();
-            if (lane == 0 && c == 0) TDX_TRACE(2, it);
-            const uint32_t a16 = a_ring16 + sa * (kAStageBytes >> 4);
-            const uint32_t b16 = b_ring16 + c * 9 * b_stage16;
-            if (elect_one()) {
-#pragma unroll
-              for (int tap = 0; tap < 6; ++tap) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const uint64_t adesc = a_hi | (uint64_t)(a16 + (tap / 3) * kPatchW + (tap % 3) + j * a_kstep16);
-                  const uint64_t bdesc = b_hi | (uint64_t)(b16 + tap * b_stage16 + j * b_kstep16);
-                  umma_bf16(d_tmem, adesc, bdesc, idesc, (c | tap | j) ? 1u : 0u);
-                }
-              }
-            }
-            __syncwarp();
-            const bool last_c = (c == nchunk - 1);
-            int sa_n = sa + 1;
-            uint32_t pha_n = pha;
-            if (sa_n == kSA) { sa_n = 0; pha_n ^= 1; }
-            a_ok = false;
-            if (!last_c || next_item < p.num_items) {
-              a_ok = mbar_test_wait(&a_full[sa_n], pha_n);
-              if (last_c) {
-                const int itn = it + 1;
-                te_ok = mbar_test_wait(&t_empty[itn & 1], ((itn >> 1) & 1) ^ 1);
-              }
-            }
-            if (elect_one()) {
-#pragma unroll
-              for (int tap = 6; tap < 9; ++tap) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const uint64_t adesc = a_hi | (uint64_t)(a16 + (tap / 3) * kPatchW + (tap % 3) + j * a_kstep16);
-                  const uint64_t bdesc = b_hi | (uint64_t)(b16 + tap * b_stage16 + j * b_kstep16);
-                  umma_bf16(d_tmem, adesc, bdesc, idesc, 1u);
-                }
-              }
-              umma_commit(&a_empty[sa]);
-              if (last_c) umma_commit(&t_full[acc]);
-            }
-            __syncwarp();
-            sa = sa_n;
-            pha = pha_n;
-          }
-          if (lane == 0) TDX_TRACE(3, it);
-          item = next_item;
-          ++it;
-          if (item >= p.num_items) break;
-        }
-        break;
-      }
       const int acc = it & 1;
       const uint32_t accph = (it >> 1) & 1;
       mbar_wait(&t_empty[acc], accph ^ 1, 300 + acc);
       tc_fence_after();
       if (lane == 0) TDX_TRACE(1, it);
       const uint32_t d_tmem = tmem_base + acc * kAccCols;
+      // (Tried and dropped: probing the next chunk's barriers between the 24th and 25th MMA of a chunk, and splitting the
+      // epilogue warps into two groups that take alternate items -- both were slower end to end on B200.)
       const bool steady = p.resident && it > 0;   // weights already in the ring: no per-stage handshakes
       uint32_t accumulate = 0;
       {
