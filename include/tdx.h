@@ -103,6 +103,23 @@ typedef struct TdxConvInDesc {
 } TdxConvInDesc;
 int tdx_conv_in_run(const TdxConvInDesc* desc, void* stream);
 
+/* The same first convolution on the tensor cores: this launch only gathers the 3x3 neighbourhood of every pixel into
+ * a bf16 NC8HW8 tensor of k_pad "channels" -- channel k = tap * ci + c for tap = 3*dy+dx in 0..8 and c in
+ * 0..ci-1 (ci = sum(src_channels) + 1, the ones channel last; zero outside the image, like the reference's padded
+ * conv), zero for k >= 9*ci -- and the convolution itself becomes a 1x1 tdx_igemm_run over that tensor with the
+ * weight matrix [c_out][k_pad] (so it gets the igemm epilogue: pixel-norm, silu, three outputs).  The inputs and
+ * weights are rounded to bf16, as in the reference's bf16 autocast of models/edm_unet.py:168-172. */
+typedef struct TdxIm2colDesc {
+  const void* src[2];        /* NCHW planar, n_img x src_channels[i] x H x W */
+  int32_t src_channels[2];   /* channels of each source (second may be 0) */
+  int32_t src_dtype[2];      /* 0 = fp32, 1 = bf16 */
+  const float* src_scale[2]; /* optional DEVICE scalar multiplied into source i, or NULL */
+  void* out;                 /* bf16 NC8HW8 [n_img][k_pad/8][H][W][8] */
+  int32_t k_pad;             /* multiple of 64, >= 9 * (sum(src_channels) + 1) */
+  int32_t n_img, height, width;
+} TdxIm2colDesc;
+int tdx_im2col_run(const TdxIm2colDesc* desc, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------------
  * Last convolution (out_conv with out_gain folded, models/edm_unet.py:179) + optionally the whole scheduler update
  * (EDMDPMSolverMultistepScheduler.step, scheduler/dpmsolver.py:650-726, closed form of SURVEY.md Appendix B):
@@ -204,6 +221,7 @@ uint64_t tdx_tile_seed(uint64_t base_seed, int64_t ty, int64_t tx);
 typedef struct TdxProgram TdxProgram;
 int tdx_program_create(TdxProgram** out);
 int tdx_program_add_conv_in(TdxProgram* p, const TdxConvInDesc* d);
+int tdx_program_add_im2col(TdxProgram* p, const TdxIm2colDesc* d);
 int tdx_program_add_igemm(TdxProgram* p, const TdxIgemmDesc* d);
 int tdx_program_add_conv_out(TdxProgram* p, const TdxConvOutDesc* d);
 int tdx_program_add_embed(TdxProgram* p, const TdxEmbedDesc* d);
@@ -214,7 +232,7 @@ int tdx_program_run(TdxProgram* p, int use_graph, void* stream);
 /* Capture + instantiate + upload the graph without running it (keeps one-time costs out of timed regions). */
 int tdx_program_instantiate(TdxProgram* p, void* stream);
 /* Eager run with a CUDA event pair around every launch: ms_per_launch[i] = device time of launch i (in program
- * order, tdx_program_num_launches entries); kinds[i] = 0 conv_in, 1 igemm, 2 conv_out, 3 embed, 4 attn.  Synchronises. */
+ * order, tdx_program_num_launches entries); kinds[i] = 0 conv_in, 1 igemm, 2 conv_out, 3 embed, 4 attn, 5 im2col.  Synchronises. */
 int tdx_program_profile(TdxProgram* p, float* ms_per_launch, int32_t* kinds, void* stream);
 int tdx_program_destroy(TdxProgram* p);
 

@@ -35,6 +35,14 @@ class TdxConvInDesc(C.Structure):
     ]
 
 
+class TdxIm2colDesc(C.Structure):
+    _fields_ = [
+        ("src", C.c_void_p * 2), ("src_channels", C.c_int32 * 2), ("src_dtype", C.c_int32 * 2),
+        ("src_scale", C.c_void_p * 2), ("out", C.c_void_p), ("k_pad", C.c_int32), ("n_img", C.c_int32),
+        ("height", C.c_int32), ("width", C.c_int32),
+    ]
+
+
 class TdxConvOutDesc(C.Structure):
     _fields_ = [
         ("x", C.c_void_p), ("c_in", C.c_int32), ("weight", C.c_void_p), ("c_out", C.c_int32), ("n_img", C.c_int32),
@@ -60,7 +68,8 @@ class TdxAttnDesc(C.Structure):
                 ("heads", C.c_int32), ("head_dim", C.c_int32), ("tokens", C.c_int32)]
 
 
-ABI_STRUCTS = [TdxOutSpec, TdxIgemmDesc, TdxConvInDesc, TdxConvOutDesc, TdxEmbedBlock, TdxEmbedDesc, TdxAttnDesc]
+ABI_STRUCTS = [TdxOutSpec, TdxIgemmDesc, TdxConvInDesc, TdxConvOutDesc, TdxEmbedBlock, TdxEmbedDesc, TdxAttnDesc,
+               TdxIm2colDesc]
 
 OUT_NONE, OUT_RAW, OUT_SILU, OUT_PNORM_SILU = 0, 1, 2, 3
 SP_SAME, SP_DOWN2, SP_UP2 = 0, 1, 2
@@ -99,7 +108,8 @@ def _declare(l: C.CDLL) -> None:
         if l.tdx_abi_sizeof(i) != C.sizeof(st):
             raise TdxError(f"ABI mismatch for {st.__name__}: C {l.tdx_abi_sizeof(i)} vs ctypes {C.sizeof(st)}")
     for name, desc in (("tdx_conv_in_run", TdxConvInDesc), ("tdx_conv_out_run", TdxConvOutDesc),
-                       ("tdx_embed_run", TdxEmbedDesc), ("tdx_attn_run", TdxAttnDesc)):
+                       ("tdx_embed_run", TdxEmbedDesc), ("tdx_attn_run", TdxAttnDesc),
+                       ("tdx_im2col_run", TdxIm2colDesc)):
         fn = getattr(l, name)
         fn.restype = C.c_int
         fn.argtypes = [C.POINTER(desc), C.c_void_p]
@@ -130,7 +140,7 @@ def _declare(l: C.CDLL) -> None:
     l.tdx_program_create.argtypes = [C.POINTER(C.c_void_p)]
     for name, desc in (("tdx_program_add_conv_in", TdxConvInDesc), ("tdx_program_add_igemm", TdxIgemmDesc),
                        ("tdx_program_add_conv_out", TdxConvOutDesc), ("tdx_program_add_embed", TdxEmbedDesc),
-                       ("tdx_program_add_attn", TdxAttnDesc)):
+                       ("tdx_program_add_attn", TdxAttnDesc), ("tdx_program_add_im2col", TdxIm2colDesc)):
         fn = getattr(l, name)
         fn.restype = C.c_int
         fn.argtypes = [C.c_void_p, C.POINTER(desc)]

@@ -120,6 +120,7 @@ extern "C" int tdx_abi_sizeof(int which) {
     case 4: return (int)sizeof(TdxEmbedBlock);
     case 5: return (int)sizeof(TdxEmbedDesc);
     case 6: return (int)sizeof(TdxAttnDesc);
+    case 7: return (int)sizeof(TdxIm2colDesc);
     default: return -1;
   }
 }

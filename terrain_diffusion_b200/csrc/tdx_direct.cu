@@ -213,6 +213,84 @@ int conv_in_launch(const TdxConvInDesc& d, cudaStream_t stream) {
   return TDX_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ im2col of the input
+struct Im2colParams {
+  const void* src[2];
+  int src_ch[2], src_dtype[2];
+  const float* src_scale[2];
+  uint4* out;
+  int ci, kpad8, H, W;
+};
+
+// Thread = one pixel x one group of 8 consecutive k (k = tap * ci + c); a warp covers 32 consecutive pixels, so the
+// source reads are coalesced rows of the planar input (L1-resident after the first k-group) and every store is 512 B.
+__global__ void __launch_bounds__(256) im2col_in_kernel(const Im2colParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int pix = blockIdx.x * 256 + threadIdx.x;
+  const int kg = blockIdx.y, img = blockIdx.z;
+  if (pix >= p.H * p.W) return;
+  const int y = pix / p.W, x = pix - y * p.W;
+  const size_t plane = (size_t)p.H * p.W;
+  const float s0 = p.src_scale[0] ? __ldg(p.src_scale[0]) : 1.0f;
+  const float s1 = p.src_scale[1] ? __ldg(p.src_scale[1]) : 1.0f;
+  const int c0n = p.src_ch[0], c1n = p.src_ch[1];
+  float v[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int k = kg * 8 + j;
+    const int tap = k / p.ci, c = k - tap * p.ci;
+    float val = 0.f;
+    if (tap < 9) {
+      const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
+      if (yy >= 0 && yy < p.H && xx >= 0 && xx < p.W) {
+        const size_t off = (size_t)yy * p.W + xx;
+        if (c < c0n) val = load_in(p.src[0], p.src_dtype[0], ((size_t)img * c0n + c) * plane + off) * s0;
+        else if (c < c0n + c1n) val = load_in(p.src[1], p.src_dtype[1], ((size_t)img * c1n + (c - c0n)) * plane + off) * s1;
+        else val = 1.0f;
+      }
+    }
+    v[j] = val;
+  }
+  uint4 u;
+  u.x = pack_bf16x2(v[0], v[1]);
+  u.y = pack_bf16x2(v[2], v[3]);
+  u.z = pack_bf16x2(v[4], v[5]);
+  u.w = pack_bf16x2(v[6], v[7]);
+  p.out[((size_t)img * p.kpad8 + kg) * plane + pix] = u;
+}
+
+int im2col_validate(const TdxIm2colDesc& d) {
+  TDX_REQUIRE(d.src[0] && d.src_channels[0] > 0, "im2col: src[0] missing");
+  TDX_REQUIRE(d.src_channels[1] == 0 || d.src[1], "im2col: src[1] missing");
+  TDX_REQUIRE(d.out, "im2col: out is null");
+  const int ci = d.src_channels[0] + d.src_channels[1] + 1;
+  TDX_REQUIRE(d.k_pad % 64 == 0 && d.k_pad >= 9 * ci, "im2col: k_pad=%d must be a multiple of 64 >= 9*%d", d.k_pad, ci);
+  TDX_REQUIRE(d.n_img >= 1 && d.n_img <= 65535 && d.height >= 1 && d.width >= 1, "im2col: bad shape");
+  return TDX_OK;
+}
+
+int im2col_launch(const TdxIm2colDesc& d, cudaStream_t stream) {
+  Im2colParams p;
+  for (int i = 0; i < 2; ++i) {
+    p.src[i] = d.src[i];
+    p.src_ch[i] = d.src_channels[i];
+    p.src_dtype[i] = d.src_dtype[i];
+    p.src_scale[i] = d.src_scale[i];
+  }
+  p.out = reinterpret_cast<uint4*>(d.out);
+  p.ci = d.src_channels[0] + d.src_channels[1] + 1;
+  p.kpad8 = d.k_pad / 8;
+  p.H = d.height;
+  p.W = d.width;
+  dim3 grid((d.height * d.width + 255) / 256, p.kpad8, d.n_img);
+  cudaLaunchConfig_t cfg;
+  cudaLaunchAttribute attr[1];
+  fill_launch_config(&cfg, attr, grid, dim3(256), 0, stream);
+  TDX_CHECK_CUDA(cudaLaunchKernelEx(&cfg, im2col_in_kernel, p));
+  return TDX_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ last conv (+ scheduler)
 struct ConvOutParams {
   const uint4* x;
@@ -540,6 +618,13 @@ extern "C" int tdx_conv_in_run(const TdxConvInDesc* d, void* stream) {
   int rc = conv_in_validate(*d);
   if (rc != TDX_OK) return rc;
   return conv_in_launch(*d, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int tdx_im2col_run(const TdxIm2colDesc* d, void* stream) {
+  if (!d) { set_error("im2col: null descriptor"); return TDX_E_INVALID; }
+  int rc = im2col_validate(*d);
+  if (rc != TDX_OK) return rc;
+  return im2col_launch(*d, reinterpret_cast<cudaStream_t>(stream));
 }
 
 extern "C" int tdx_conv_out_run(const TdxConvOutDesc* d, void* stream) {

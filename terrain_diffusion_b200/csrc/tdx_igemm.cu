@@ -571,7 +571,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CU
         float rscale = p.resid_scale;
         if (has_resid) resid_fetch(tw);   // issued before the accumulator wait: overlaps the MMAs of this item
         const uint4* rbase = rbase_pre;
-        if (has_resid && p.resid_pnorm) {
+        if (has_resid && p.resid_pnorm && !(p.dbg & 32)) {
           // the residual's pixel-norm runs over ALL Cout channels: the kWQ warps of a pixel quadrant each read their
           // share of the 8-channel planes (C8 is a multiple of 8) and combine through shared memory
           float ss = 0.f;
@@ -604,7 +604,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CU
 #pragma unroll
         for (int o = 0; o < 3; ++o) {
           const int sp = p.out[o].spatial;
-          oact[o] = (p.out[o].kind != TDX_OUT_NONE) && valid && !(sp == TDX_SP_DOWN2 && ((Y | X) & 1));
+          oact[o] = (p.out[o].kind != TDX_OUT_NONE) && valid && !(sp == TDX_SP_DOWN2 && ((Y | X) & 1)) && !(p.dbg & 16);
           const uint32_t oplane = sp == TDX_SP_DOWN2 ? (plane >> 2) : (sp == TDX_SP_UP2 ? (plane << 2) : plane);
           optr[o] = reinterpret_cast<uint4*>(p.out[o].ptr) + pixel_off(sp) + (size_t)(chbase >> 3) * oplane;
         }
@@ -622,7 +622,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CU
           if (p.epi & TDX_EPI_EMB_SILU) {
 #pragma unroll
             for (int i = 0; i < kChunk; i += 4) {
-              float4 c4 = __ldg(reinterpret_cast<const float4*>(cvb + ck * kChunk + i));
+              const float4 c4 = __ldg(reinterpret_cast<const float4*>(cvb + ck * kChunk + i));
               v[i + 0] = mp_silu_f(v[i + 0] * c4.x);
               v[i + 1] = mp_silu_f(v[i + 1] * c4.y);
               v[i + 2] = mp_silu_f(v[i + 2] * c4.z);
@@ -656,7 +656,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CU
 #pragma unroll
           for (int o = 0; o < 3; ++o) {
             const int kind = p.out[o].kind, sp = p.out[o].spatial;
-            if (kind == TDX_OUT_NONE) continue;
+            if (kind == TDX_OUT_NONE || ((p.dbg & 64) && o > 0)) continue;
             float hs = 0.5f * p.out[o].scale;
             if (kind == TDX_OUT_PNORM_SILU) hs = (p.epi & TDX_EPI_PNORM) ? 0.5f : 0.5f * inv;
             const uint32_t oplane = sp == TDX_SP_DOWN2 ? (plane >> 2) : (sp == TDX_SP_UP2 ? (plane << 2) : plane);

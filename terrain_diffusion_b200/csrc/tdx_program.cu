@@ -1,4 +1,4 @@
-// Program = recorded launch list (conv_in / igemm / conv_out / embed) with pre-built TMA descriptors, replayed through
+// Program = recorded launch list (conv_in / im2col / igemm / conv_out / embed / attn) with pre-built TMA descriptors, replayed through
 // one CUDA graph.  Host-side only; all kernels live in tdx_igemm.cu / tdx_direct.cu.
 #include <vector>
 
@@ -10,6 +10,8 @@ int igemm_prepare();
 int igemm_launch(const TdxIgemmDesc& d, const CUtensorMap* tms, cudaStream_t stream);
 int conv_in_validate(const TdxConvInDesc& d);
 int conv_in_launch(const TdxConvInDesc& d, cudaStream_t stream);
+int im2col_validate(const TdxIm2colDesc& d);
+int im2col_launch(const TdxIm2colDesc& d, cudaStream_t stream);
 int conv_out_validate(const TdxConvOutDesc& d);
 int conv_out_launch(const TdxConvOutDesc& d, cudaStream_t stream);
 int embed_validate(const TdxEmbedDesc& d);
@@ -19,7 +21,7 @@ int attn_prepare();
 int attn_launch(const TdxAttnDesc& d, cudaStream_t stream);
 int embed_launch(const TdxEmbedDesc& d, cudaStream_t stream);
 
-enum OpType { OP_CONV_IN, OP_IGEMM, OP_CONV_OUT, OP_EMBED, OP_ATTN };
+enum OpType { OP_CONV_IN, OP_IGEMM, OP_CONV_OUT, OP_EMBED, OP_ATTN, OP_IM2COL };
 
 struct Op {
   OpType type;
@@ -29,6 +31,7 @@ struct Op {
   TdxConvOutDesc co;
   TdxEmbedDesc em;
   TdxAttnDesc at;
+  TdxIm2colDesc im;
   std::vector<TdxEmbedBlock> blocks;
 };
 }  // namespace tdx
@@ -53,6 +56,7 @@ static int launch_all(TdxProgram* p, cudaStream_t stream) {
         rc = embed_launch(op.em, stream);
         break;
       case OP_ATTN: rc = attn_launch(op.at, stream); break;
+      case OP_IM2COL: rc = im2col_launch(op.im, stream); break;
     }
     if (rc != TDX_OK) return rc;
   }
@@ -80,6 +84,17 @@ extern "C" int tdx_program_add_conv_in(TdxProgram* p, const TdxConvInDesc* d) {
   Op op;
   op.type = OP_CONV_IN;
   op.ci = *d;
+  p->ops.push_back(op);
+  return invalidate_graph(p);
+}
+
+extern "C" int tdx_program_add_im2col(TdxProgram* p, const TdxIm2colDesc* d) {
+  TDX_REQUIRE(p && d, "program_add_im2col: null argument");
+  int rc = im2col_validate(*d);
+  if (rc != TDX_OK) return rc;
+  Op op;
+  op.type = OP_IM2COL;
+  op.im = *d;
   p->ops.push_back(op);
   return invalidate_graph(p);
 }
@@ -209,6 +224,7 @@ extern "C" int tdx_program_profile(TdxProgram* p, float* ms_per_launch, int32_t*
         rc = embed_launch(op.em, stream);
         break;
       case OP_ATTN: rc = attn_launch(op.at, stream); break;
+      case OP_IM2COL: rc = im2col_launch(op.im, stream); break;
     }
     cudaEventRecord(ev[i + 1], stream);
     if (kinds) kinds[i] = (int32_t)op.type;

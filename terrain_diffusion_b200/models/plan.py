@@ -19,6 +19,7 @@ sub-sampled or nearest-x2 up-sampled) and the decoder-side activated skip.  Weig
 from __future__ import annotations
 
 import ctypes as C
+import os
 import math
 
 import numpy as np
@@ -146,6 +147,13 @@ class FoldedWeights:
         first = enc[0]
         w_in = effective_weight(sd[f"enc.{first['name']}.weight"])               # [cout][ci][3][3]
         g["conv_in"] = w_in.permute(2, 3, 1, 0).reshape(9, w_in.shape[1], w_in.shape[0]).contiguous()  # [tap][ci][cout]
+        # the same weights as the [cout][k_pad] matrix of the tensor-core path (tdx_im2col_run + 1x1 igemm):
+        # k = tap * ci + c, zero-padded to a multiple of 64
+        ci = w_in.shape[1]
+        self.conv_in_kpad = ((9 * ci + 63) // 64) * 64
+        w_mat = torch.zeros((w_in.shape[0], self.conv_in_kpad, 1, 1), dtype=torch.float32, device=device)
+        w_mat[:, :9 * ci, 0, 0] = w_in.permute(0, 2, 3, 1).reshape(w_in.shape[0], 9 * ci)
+        self.segs["conv_in.im2col"] = [w_mat]
         out_gain = sd["out_gain"] if "out_gain" in sd else 1.0
         w_out = effective_weight(sd["out_conv.weight"], gain=out_gain)                  # [cout<=8][c][3][3]
         wpad = 1 if w_out.shape[0] == 1 else 8
@@ -249,6 +257,8 @@ class UNetEmitter:
             raise ValueError(f"spatial size {h}x{w} must be a multiple of {need} for this model")
         self.fw, self.n, self.h, self.w = fw, n, h, w
         self.dev = fw.device
+        # TDX_CONV_IN_DIRECT=1 selects the CUDA-core first convolution (fp32 inputs / weights) instead of im2col + igemm
+        self.conv_in_direct = os.environ.get("TDX_CONV_IN_DIRECT") == "1"
         self.arena: dict = {}
         self.cvecs: dict = {}
 
@@ -429,12 +439,30 @@ class UNetEmitter:
                     cd.src_scale[i] = scale.data_ptr() if scale is not None else None
                     tot += ch
                 assert tot + 1 == b["cin"], (tot, b["cin"])
-                cd.weight = g["conv_in"].data_ptr()
-                cd.c_out = cout
-                cd.n_img, cd.height, cd.width = n, h, w
-                cur = self._emit_outputs(cd, key, cout, h, w, nxt, enc_index)
-                L.check(L.lib().tdx_program_add_conv_in(prog.handle, C.byref(cd)))
-                prog.n_launch += 1
+                if self.conv_in_direct:
+                    # CUDA-core first convolution (fp32 inputs and weights): kept for parity experiments
+                    cd.weight = g["conv_in"].data_ptr()
+                    cd.c_out = cout
+                    cd.n_img, cd.height, cd.width = n, h, w
+                    cur = self._emit_outputs(cd, key, cout, h, w, nxt, enc_index)
+                    L.check(L.lib().tdx_program_add_conv_in(prog.handle, C.byref(cd)))
+                    prog.n_launch += 1
+                else:
+                    # tensor-core first convolution: gather the 3x3 neighbourhoods (tdx_im2col_run), then a 1x1 igemm
+                    im = L.TdxIm2colDesc()
+                    for i in range(2):
+                        im.src[i], im.src_channels[i] = cd.src[i], cd.src_channels[i]
+                        im.src_dtype[i], im.src_scale[i] = cd.src_dtype[i], cd.src_scale[i]
+                    kpad = fw.conv_in_kpad
+                    cols = self.act(key + "im2col", kpad, h, w)
+                    im.out = cols.data_ptr()
+                    im.k_pad = kpad
+                    im.n_img, im.height, im.width = n, h, w
+                    L.check(L.lib().tdx_program_add_im2col(prog.handle, C.byref(im)))
+                    prog.n_launch += 1
+                    d = self._igemm(prog, [(cols, kpad, 1)], "conv_in.im2col", cout, h, w)
+                    cur = self._emit_outputs(d, key, cout, h, w, nxt, enc_index)
+                    self._add_igemm(prog, d)
             elif b["mode"] == "enc":
                 resid_sp = L.SP_SAME
                 if b["resample"] == "down":
