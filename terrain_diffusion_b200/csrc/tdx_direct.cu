@@ -10,6 +10,7 @@ __device__ __forceinline__ float mp_silu_precise(float x) { return x / (1.0f + e
 
 // ------------------------------------------------------------------------------------------------ first conv
 constexpr int kConvInGroups = 4;   // 32-pixel groups per block (amortises the weight staging)
+constexpr int kConvOutGroups = 1;  // conv_out stages only 9*C*COUT weights: more, smaller blocks keep every SM busy
 
 struct ConvInParams {
   const void* src[2];
@@ -222,42 +223,69 @@ struct Im2colParams {
   int ci, kpad8, H, W;
 };
 
-// Thread = one pixel x one group of 8 consecutive k (k = tap * ci + c); a warp covers 32 consecutive pixels, so the
-// source reads are coalesced rows of the planar input (L1-resident after the first k-group) and every store is 512 B.
-__global__ void __launch_bounds__(256) im2col_in_kernel(const Im2colParams p) {
+// Thread = one pixel, all k (k = tap * CI + c); CI is a template constant, so the (tap, c) of every k is known at
+// compile time and the gather is straight-line code: 9*(CI-1) coalesced source reads and k_pad/8 16-byte stores
+// (a warp covers 32 consecutive pixels: 512 B per store instruction).
+template <int CI>
+__global__ void __launch_bounds__(128) im2col_in_kernel(const Im2colParams p) {
   pdl_launch_dependents();
   pdl_wait();
-  const int pix = blockIdx.x * 256 + threadIdx.x;
-  const int kg = blockIdx.y, img = blockIdx.z;
+  const int pix = blockIdx.x * 128 + threadIdx.x;
+  const int img = blockIdx.y;
   if (pix >= p.H * p.W) return;
   const int y = pix / p.W, x = pix - y * p.W;
   const size_t plane = (size_t)p.H * p.W;
+  const int c0n = p.src_ch[0], c1n = p.src_ch[1];
+  // per input channel: base pointer of this image's plane, element type, scale
+  const uint8_t* cbase[CI - 1];
+  int cdt[CI - 1];
+  float csc[CI - 1];
   const float s0 = p.src_scale[0] ? __ldg(p.src_scale[0]) : 1.0f;
   const float s1 = p.src_scale[1] ? __ldg(p.src_scale[1]) : 1.0f;
-  const int c0n = p.src_ch[0], c1n = p.src_ch[1];
-  float v[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int k = kg * 8 + j;
-    const int tap = k / p.ci, c = k - tap * p.ci;
-    float val = 0.f;
-    if (tap < 9) {
-      const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
-      if (yy >= 0 && yy < p.H && xx >= 0 && xx < p.W) {
-        const size_t off = (size_t)yy * p.W + xx;
-        if (c < c0n) val = load_in(p.src[0], p.src_dtype[0], ((size_t)img * c0n + c) * plane + off) * s0;
-        else if (c < c0n + c1n) val = load_in(p.src[1], p.src_dtype[1], ((size_t)img * c1n + (c - c0n)) * plane + off) * s1;
-        else val = 1.0f;
-      }
-    }
-    v[j] = val;
+  for (int c = 0; c < CI - 1; ++c) {
+    const int which = c < c0n ? 0 : 1;
+    const int cc = which ? c - c0n : c;
+    const int cn = which ? c1n : c0n;
+    cdt[c] = p.src_dtype[which];
+    csc[c] = which ? s1 : s0;
+    cbase[c] = reinterpret_cast<const uint8_t*>(p.src[which]) + ((size_t)img * cn + cc) * plane * (cdt[c] == 0 ? 4 : 2);
   }
-  uint4 u;
-  u.x = pack_bf16x2(v[0], v[1]);
-  u.y = pack_bf16x2(v[2], v[3]);
-  u.z = pack_bf16x2(v[4], v[5]);
-  u.w = pack_bf16x2(v[6], v[7]);
-  p.out[((size_t)img * p.kpad8 + kg) * plane + pix] = u;
+  bool ok[9];
+  int off[9];
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap) {
+    const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
+    ok[tap] = yy >= 0 && yy < p.H && xx >= 0 && xx < p.W;
+    off[tap] = yy * p.W + xx;
+  }
+  constexpr int KPAD = ((9 * CI + 63) / 64) * 64;
+  uint4* dst = p.out + (size_t)img * (KPAD / 8) * plane + pix;
+#pragma unroll
+  for (int kg = 0; kg < KPAD / 8; ++kg) {
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = kg * 8 + j;        // compile-time after unrolling
+      const int tap = k / CI, c = k % CI;
+      float val = 0.f;
+      if (tap < 9) {
+        if (c == CI - 1) {
+          val = ok[tap] ? 1.0f : 0.f;
+        } else if (ok[tap]) {
+          val = (cdt[c] == 0 ? __ldg(reinterpret_cast<const float*>(cbase[c]) + off[tap])
+                             : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(cbase[c])[off[tap]])) * csc[c];
+        }
+      }
+      v[j] = val;
+    }
+    uint4 u;
+    u.x = pack_bf16x2(v[0], v[1]);
+    u.y = pack_bf16x2(v[2], v[3]);
+    u.z = pack_bf16x2(v[4], v[5]);
+    u.w = pack_bf16x2(v[6], v[7]);
+    dst[(size_t)kg * plane] = u;
+  }
 }
 
 int im2col_validate(const TdxIm2colDesc& d) {
@@ -265,7 +293,10 @@ int im2col_validate(const TdxIm2colDesc& d) {
   TDX_REQUIRE(d.src_channels[1] == 0 || d.src[1], "im2col: src[1] missing");
   TDX_REQUIRE(d.out, "im2col: out is null");
   const int ci = d.src_channels[0] + d.src_channels[1] + 1;
-  TDX_REQUIRE(d.k_pad % 64 == 0 && d.k_pad >= 9 * ci, "im2col: k_pad=%d must be a multiple of 64 >= 9*%d", d.k_pad, ci);
+  TDX_REQUIRE(ci == 6 || ci == 12, "im2col: %d input channels; instantiated for 5 (decoder / latent models) or 11 "
+              "(coarse model)", ci - 1);
+  TDX_REQUIRE(d.k_pad == ((9 * ci + 63) / 64) * 64, "im2col: k_pad=%d must be 9*%d rounded up to a multiple of 64",
+              d.k_pad, ci);
   TDX_REQUIRE(d.n_img >= 1 && d.n_img <= 65535 && d.height >= 1 && d.width >= 1, "im2col: bad shape");
   return TDX_OK;
 }
@@ -283,11 +314,12 @@ int im2col_launch(const TdxIm2colDesc& d, cudaStream_t stream) {
   p.kpad8 = d.k_pad / 8;
   p.H = d.height;
   p.W = d.width;
-  dim3 grid((d.height * d.width + 255) / 256, p.kpad8, d.n_img);
+  dim3 grid((d.height * d.width + 127) / 128, d.n_img);
   cudaLaunchConfig_t cfg;
   cudaLaunchAttribute attr[1];
-  fill_launch_config(&cfg, attr, grid, dim3(256), 0, stream);
-  TDX_CHECK_CUDA(cudaLaunchKernelEx(&cfg, im2col_in_kernel, p));
+  fill_launch_config(&cfg, attr, grid, dim3(128), 0, stream);
+  if (p.ci == 6) TDX_CHECK_CUDA(cudaLaunchKernelEx(&cfg, im2col_in_kernel<6>, p));
+  else TDX_CHECK_CUDA(cudaLaunchKernelEx(&cfg, im2col_in_kernel<12>, p));
   return TDX_OK;
 }
 
@@ -325,8 +357,8 @@ __global__ void __launch_bounds__(128) conv_out_kernel(const ConvOutParams p) {
   const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
   const int sub = lane >> 3;                                // 0..3
   const size_t plane = (size_t)p.H * p.W;
-  for (int grp = 0; grp < kConvInGroups; ++grp) {
-    const int pix = (blockIdx.x * kConvInGroups + grp) * 32 + wq * 8 + (lane & 7);
+  for (int grp = 0; grp < kConvOutGroups; ++grp) {
+    const int pix = (blockIdx.x * kConvOutGroups + grp) * 32 + wq * 8 + (lane & 7);
     const bool inb = pix < p.H * p.W;
     const int y = inb ? pix / p.W : 0, x = inb ? pix % p.W : 0;
     float acc[COUT];
@@ -345,10 +377,10 @@ __global__ void __launch_bounds__(128) conv_out_kernel(const ConvOutParams p) {
         const float* w = ws + (tap * C + g * 8) * COUT;
         if (COUT == 1) {
           const float4 wa = *reinterpret_cast<const float4*>(w), wb = *reinterpret_cast<const float4*>(w + 4);
-          acc[0] = fmaf(wa.x, a[0], acc[0]); acc[0] = fmaf(wa.y, a[1], acc[0]);
-          acc[0] = fmaf(wa.z, a[2], acc[0]); acc[0] = fmaf(wa.w, a[3], acc[0]);
-          acc[0] = fmaf(wb.x, a[4], acc[0]); acc[0] = fmaf(wb.y, a[5], acc[0]);
-          acc[0] = fmaf(wb.z, a[6], acc[0]); acc[0] = fmaf(wb.w, a[7], acc[0]);
+          // (a tree per load instead of one 144-deep FMA chain through acc[0])
+          const float t0 = fmaf(wa.x, a[0], wa.y * a[1]), t1 = fmaf(wa.z, a[2], wa.w * a[3]);
+          const float t2 = fmaf(wb.x, a[4], wb.y * a[5]), t3 = fmaf(wb.z, a[6], wb.w * a[7]);
+          acc[0] += (t0 + t1) + (t2 + t3);
         } else {
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
@@ -420,7 +452,7 @@ int conv_out_launch(const TdxConvOutDesc& d, cudaStream_t stream) {
   const int smem = 9 * d.c_in * wout * 4;
   int rc_prep = direct_prepare();
   if (rc_prep != TDX_OK) return rc_prep;
-  dim3 grid((d.height * d.width + 32 * kConvInGroups - 1) / (32 * kConvInGroups), d.n_img);
+  dim3 grid((d.height * d.width + 32 * kConvOutGroups - 1) / (32 * kConvOutGroups), d.n_img);
   cudaLaunchConfig_t cfg;
   cudaLaunchAttribute attr[1];
   fill_launch_config(&cfg, attr, grid, dim3(128), smem, stream);
