@@ -330,7 +330,9 @@ def main():
             peak, peak_src = 1400.0, "fallback (B200_PROFILING.md sustained ~1.4 PFLOP/s)"
         traffic = None
         try:
-            traffic = json.loads((ROOT / "profiles" / "igemm_traffic.json").read_text()).get("dram_bytes_per_launch")
+            tj = json.loads((ROOT / "profiles" / "igemm_traffic.json").read_text())
+            if tj.get("workload_tiles", 1) == args.tiles:   # the ncu capture is of the default (1-tile) workload
+                traffic = tj.get("dram_bytes_per_launch")
         except Exception:
             pass
         roof = {"bound": "tensor", "kernel": "tdx::igemm_kernel (tcgen05 implicit-GEMM conv)", "achieved": achieved,
