@@ -126,3 +126,27 @@ def test_scheduler_tables_and_errors_on_cpu():
         s.step(torch.zeros(1), s.timesteps[0], torch.zeros(1))
     with pytest.raises(NotImplementedError):
         EDMDPMSolverMultistepScheduler(solver_order=3)
+
+
+def test_first_convolution_weight_matrix_of_the_im2col_path_reproduces_the_3x3_convolution():
+    """FoldedWeights lays the first MPConv's effective weights out as [cout][k_pad] with k = tap*ci + c, the channel order
+    tdx_im2col_run writes (include/tdx.h): unfold(cat([x, ones])) @ W^T must equal conv2d(cat([x, ones]), w, padding=1)."""
+    import torch.nn.functional as F
+
+    from terrain_diffusion_b200.models.plan import FoldedWeights
+    cfg = ounet.DECODER_CFG
+    m = EDMUnet2D(**cfg).eval()
+    m.load_state_dict(ounet.procedural_state_dict(cfg, seed=3))
+    fw = FoldedWeights(m, torch.device("cpu"))
+    first = fw.enc[0]["name"]
+    w_in = effective_weight(m.state_dict()[f"enc.{first}.weight"].float())       # [cout][ci][3][3]
+    ci = w_in.shape[1]
+    assert fw.conv_in_kpad == 64 and ci == 6
+    w_mat = fw.segs["conv_in.im2col"][0]
+    assert tuple(w_mat.shape) == (w_in.shape[0], 64, 1, 1) and torch.count_nonzero(w_mat[:, 9 * ci:]) == 0
+    g = torch.Generator().manual_seed(0)
+    x = torch.cat([torch.randn(2, ci - 1, 12, 10, generator=g), torch.ones(2, 1, 12, 10)], dim=1)
+    cols = F.unfold(x, kernel_size=3, padding=1).view(2, ci, 9, 12, 10).permute(0, 2, 1, 3, 4).reshape(2, 9 * ci, 12, 10)
+    got = torch.einsum("ok,nkhw->nohw", w_mat[:, :9 * ci, 0, 0], cols)
+    ref = F.conv2d(x, w_in, padding=1)
+    assert torch.allclose(got, ref, atol=1e-5, rtol=1e-5)
