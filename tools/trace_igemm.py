@@ -1,4 +1,11 @@
-"""Per-tile phase timeline of CTA 0 of the igemm kernel (debug hook tdx_debug_set_igemm_trace)."""
+"""Per-tile phase timeline of CTA 0 of the igemm kernel (debug hook tdx_debug_set_igemm_trace).
+
+    python tools/trace_igemm.py [flags]      # flags = OR of the kernel's ablation bits (tdx_debug_set_igemm_flags):
+        1  A descriptors with SBO=128 (wrong results; smem bank-conflict experiment)     2  no weight loads
+        4  epilogue does nothing      8  no epilogue warps      16  compute everything, store nothing
+        32 skip the residual pixel-norm pre-pass      64 only output 0 is produced
+    python tools/trace_igemm.py floor        # launch floor of an empty-ish kernel
+"""
 import ctypes as C
 import os
 import sys
