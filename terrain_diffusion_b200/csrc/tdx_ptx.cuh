@@ -50,20 +50,6 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Non-blocking probe (try_wait may suspend the thread for a while before reporting failure; test_wait never does).
-__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t"
-      ".reg .pred P;\n\t"
-      "mbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
-      "selp.b32 %0, 1, 0, P;\n\t"
-      "}\n"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
 // Bounded wait: a broken pipeline traps (visible as a CUDA error on the host) instead of hanging the GPU box.
 #ifndef TDX_WAIT_LIMIT
 #define TDX_WAIT_LIMIT (1ll << 31)   // ~1 s of SM clocks
