@@ -200,6 +200,30 @@ int tdx_canvas_add(float* dst, int32_t channels, int32_t dst_h, int32_t dst_w, c
  * divide by sigma_data afterwards, sample_diffusion_decoder.py:211).  divisor == 1 skips the second division. */
 int tdx_blend_normalize(float* out, const float* canvas_val, const float* canvas_w, int32_t channels, int64_t plane,
                         float divisor, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Elevation read-out (WorldPipeline._compute_elev, inference/world_pipeline.py:1277-1313): the reference normalises
+ * the canvases on read and runs data/laplacian_encoder.py (torchvision resize + gaussian_blur) on the CPU for every
+ * get().  These five fp32 primitives keep it on the device; terrain_diffusion_b200/inference/postproc.py composes them
+ * exactly like laplacian_decode / laplacian_encode / laplacian_denoise.  All tensors are contiguous [h][w] fp32 unless a
+ * pitch (in elements) is given.
+ * ------------------------------------------------------------------------------------------------------------------ */
+/* out = num / den * scale + offset   (world_pipeline.py:1301-1304: (sum x*w)/(sum w) * STD + MEAN) */
+int tdx_post_normalize(const float* num, const float* den, int64_t pitch, float* out, int32_t h, int32_t w, float scale,
+                       float offset, void* stream);
+/* pad_linear_extrapolation (laplacian_encoder.py:6-40): out is (h+2) x (w+2) */
+int tdx_post_pad_extrapolate(const float* x, int32_t h, int32_t w, float* out, void* stream);
+/* One axis of TF.resize(..., BILINEAR) = torch interpolate(bilinear, align_corners=False, antialias=True): axis 1
+ * resizes the width to out_size ([h][w] -> [h][out_size]), axis 0 the height.  torch resizes the width first. */
+int tdx_resize_aa_axis(const float* x, int32_t h, int32_t w, float* out, int32_t out_size, int32_t axis, void* stream);
+/* TF.gaussian_blur(x, kernel_size, sigma): reflect padding, outer product of two normalised 1-D Gaussians. */
+int tdx_gaussian_blur(const float* x, int32_t h, int32_t w, float* out, int32_t ksize, float sigma, void* stream);
+/* out[y][x] = f(a[y][x] + b[y][x]) over an h x w window of two pitched tensors (pass the pointers of the window's
+ * first element): f = identity (laplacian_decode, laplacian_encoder.py:131) or sign(v) v^2 (world_pipeline.py:1312);
+ * out_i16 (optional) additionally receives clip(floor(v), -32768, 32767) (api.py:73-77).  out or out_i16 may be NULL. */
+int tdx_post_combine(const float* a, int64_t a_pitch, const float* b, int64_t b_pitch, float* out, int16_t* out_i16,
+                     int32_t h, int32_t w, int32_t signed_square, void* stream);
+
 /* Tile-seeded N(0,1) field, bit-exact with inference/portable_rng.py + world_pipeline.py:66-115 */
 int tdx_noise_patch(uint64_t base_seed, int64_t y0, int64_t x0, int32_t h, int32_t w, int32_t channels,
                     int32_t tile_h, int32_t tile_w, float* out, void* workspace, int64_t workspace_bytes,

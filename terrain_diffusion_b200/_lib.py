@@ -125,6 +125,18 @@ def _declare(l: C.CDLL) -> None:
     l.tdx_blend_normalize.restype = C.c_int
     l.tdx_blend_normalize.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_float,
                                       C.c_void_p]
+    l.tdx_post_normalize.restype = C.c_int
+    l.tdx_post_normalize.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int32, C.c_float,
+                                     C.c_float, C.c_void_p]
+    l.tdx_post_pad_extrapolate.restype = C.c_int
+    l.tdx_post_pad_extrapolate.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
+    l.tdx_resize_aa_axis.restype = C.c_int
+    l.tdx_resize_aa_axis.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
+    l.tdx_gaussian_blur.restype = C.c_int
+    l.tdx_gaussian_blur.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_float, C.c_void_p]
+    l.tdx_post_combine.restype = C.c_int
+    l.tdx_post_combine.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32,
+                                   C.c_int32, C.c_int32, C.c_void_p]
     l.tdx_noise_patch.restype = C.c_int
     l.tdx_noise_patch.argtypes = [C.c_uint64, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                   C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]

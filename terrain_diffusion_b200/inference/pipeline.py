@@ -3,7 +3,8 @@ exactly like WorldPipeline._build_coarse_stage / _build_latent_stage / _build_de
 (reference inference/world_pipeline.py:961-992, 1133-1203, 1244-1270), with every stage on the GPU.
 
 What is NOT here (out of the hot-path scope): the Perlin/WorldClim conditioning synthesis (pass a
-`conditioning_fn(i1, i2, j1, j2) -> [5, h, w]`), climate/elevation post-processing (laplacian decode, lapse rates), HDF5
+`conditioning_fn(i1, i2, j1, j2) -> [5, h, w]`), climate post-processing (lapse rates; the elevation read-out IS here:
+`get_elev`), HDF5
 tile stores, the CLI / HTTP front-ends.  Window geometry, seeds, phase times and batching follow the reference.
 """
 from __future__ import annotations
@@ -81,6 +82,15 @@ class TerrainPipeline:
         self.residual = LazyCanvas(2, f_dec, TensorWindow((2, T, T), (2, S, S)), dev, args=(self.latents,),
                                    args_windows=(TensorWindow((6, T // self.lc, T // self.lc),
                                                               (6, S // self.lc, S // self.lc)),))
+
+    def get_elev(self, i1: int, j1: int, i2: int, j2: int, residual_mean: float, residual_std: float,
+                 as_int16: bool = False):
+        """Elevation in metres over pixel rows [i1,i2) x columns [j1,j2), computed on the device: the `elev` entry of
+        WorldPipeline.get (reference inference/world_pipeline.py:1277-1313, 1367-1384; residual_mean / residual_std are
+        the reference's model kwargs).  With as_int16 also returns the int16 tensor the HTTP API ships (api.py:73-77)."""
+        from .postproc import compute_elev
+        return compute_elev(self.residual, self.latents, i1, j1, i2, j2, self.lc, residual_mean, residual_std,
+                            as_int16=as_int16)
 
     def residual_normalized(self, i1: int, j1: int, i2: int, j2: int) -> torch.Tensor:
         """Blended decoder output over pixel rows [i1,i2) x columns [j1,j2): residual[0] / residual[1]."""

@@ -1,0 +1,68 @@
+"""Post step (elevation read-out), CPU side: the oracle restatement against the golden vectors recorded from the
+reference's own laplacian_encoder.py / WorldPipeline._compute_elev (tests/golden/make_golden_post.py), and the integer
+window geometry of the product host code against the oracle."""
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from oracle import postproc as P
+from tests._post_inputs import (ELEV_WINDOWS, RESIDUAL_MEAN, RESIDUAL_STD, elev_canvases, laplacian_case)
+
+G = np.load(Path(__file__).resolve().parent / "golden" / "post_golden.npz")
+
+
+def rel(a, b):
+    return float(np.abs(a - b).max() / (np.abs(b).max() + 1e-30))
+
+
+@pytest.mark.parametrize("name", ["rect", "square", "wide"])
+def test_oracle_laplacian_functions_match_reference_golden(name):
+    r, l = laplacian_case(name)
+    assert rel(P.laplacian_decode(r, l, extrapolate=True), G[f"lap_{name}_decode_extrap"]) < 2e-6
+    _, l2 = P.laplacian_denoise(r, l, 5)
+    # an int size means "shorter edge": the non-square cases come out with the reference's (distorted) low-res shape
+    assert l2.shape == G[f"lap_{name}_lowres"].shape
+    assert rel(l2, G[f"lap_{name}_lowres"]) < 2e-6
+    assert rel(P.laplacian_decode(r, l2), G[f"lap_{name}_elev"]) < 2e-6
+
+
+@pytest.mark.parametrize("name", list(ELEV_WINDOWS))
+def test_oracle_compute_elev_matches_reference_golden(name):
+    resid, lat = elev_canvases()
+    i1, j1, i2, j2 = ELEV_WINDOWS[name]
+    e = P.compute_elev(i1, j1, i2, j2, resid.planes, lat.planes, 8, RESIDUAL_MEAN, RESIDUAL_STD)
+    g = G[f"elev_{name}"]
+    assert e.shape == g.shape == (i2 - i1, j2 - j1)
+    assert rel(e, g) < 2e-6
+    i16 = P.elev_to_int16(g)
+    assert i16.dtype == np.dtype("<i2") and int(i16.max()) <= 32767 and np.array_equal(i16, np.floor(g).astype(np.int16))
+
+
+def test_padded_window_integer_geometry_is_identical_in_product_and_oracle():
+    from terrain_diffusion_b200.inference import postproc as H
+    rng = np.random.RandomState(0)
+    for _ in range(500):
+        i1, j1 = int(rng.randint(-5000, 5000)), int(rng.randint(-5000, 5000))
+        i2, j2 = i1 + int(rng.randint(1, 700)), j1 + int(rng.randint(1, 700))
+        for scale in (4, 8):
+            got = H.padded_window(i1, j1, i2, j2, scale)
+            assert got == P.padded_window(i1, j1, i2, j2, scale)
+            pi1, pj1, pi2, pj2 = got
+            assert pi1 % scale == pj1 % scale == pi2 % scale == pj2 % scale == 0
+            assert pi1 <= i1 - 6 * scale and pi2 >= i2 + 6 * scale and pi1 > i1 - 7 * scale - 1
+    # torchvision's int-size rule (shorter edge): the cases the goldens exercise
+    assert H._resized_output_size(96, 80, 10) == (12, 10)
+    assert H._resized_output_size(64, 136, 17) == (17, 36)
+    assert H._resized_output_size(128, 128, 16) == (16, 16)
+
+
+def test_read_out_refuses_cpu_tensors():
+    import torch
+
+    from terrain_diffusion_b200 import _lib as L
+    from terrain_diffusion_b200.inference import postproc as H
+    with pytest.raises(L.TdxError):
+        H.resize_bilinear(torch.zeros(8, 8), (16, 16))
+    with pytest.raises(L.TdxError):
+        H.gaussian_blur(torch.zeros(16, 16), 11, 5.0)
