@@ -23,7 +23,7 @@ class TerrainPipeline:
     def __init__(self, coarse_model, base_model, decoder_model, seed: int, conditioning_fn, *, coarse_means, coarse_stds,
                  cond_snr, histogram_raw, latents_means, latents_stds, latents_batch_size: int = 16,
                  decoder_tile_size: int = 512, decoder_tile_stride: int = 384, latent_compression: int = 8,
-                 t_inter: float | None = None):
+                 t_inter: float | None = None, residual_mean: float | None = None, residual_std: float | None = None):
         self.device = decoder_model.device
         self.seed = int(seed)
         self.coarse_model, self.base_model, self.decoder_model = coarse_model, base_model, decoder_model
@@ -34,6 +34,7 @@ class TerrainPipeline:
         self.lat_means = torch.as_tensor(latents_means, dtype=torch.float32)
         self.lat_stds = torch.as_tensor(latents_stds, dtype=torch.float32)
         self.lc = latent_compression
+        self.residual_mean, self.residual_std = residual_mean, residual_std   # the reference's model kwargs
         sched = EDMDPMSolverMultistepScheduler(sigma_min=0.002, sigma_max=80, sigma_data=0.5)
         self.t_init = math.atan(float(sched.sigmas[0]) / 0.5)
         self.t_inter = math.atan(0.35 / 0.5) if t_inter is None else t_inter   # world_pipeline.py:1144-1145
@@ -83,14 +84,27 @@ class TerrainPipeline:
                                    args_windows=(TensorWindow((6, T // self.lc, T // self.lc),
                                                               (6, S // self.lc, S // self.lc)),))
 
-    def get_elev(self, i1: int, j1: int, i2: int, j2: int, residual_mean: float, residual_std: float,
-                 as_int16: bool = False):
+    def get_elev(self, i1: int, j1: int, i2: int, j2: int, residual_mean: float | None = None,
+                 residual_std: float | None = None, as_int16: bool = False):
         """Elevation in metres over pixel rows [i1,i2) x columns [j1,j2), computed on the device: the `elev` entry of
         WorldPipeline.get (reference inference/world_pipeline.py:1277-1313, 1367-1384; residual_mean / residual_std are
-        the reference's model kwargs).  With as_int16 also returns the int16 tensor the HTTP API ships (api.py:73-77)."""
+        the reference's model kwargs, given here or to the constructor).  With as_int16 also returns the int16 tensor
+        the HTTP API ships (api.py:73-77)."""
         from .postproc import compute_elev
-        return compute_elev(self.residual, self.latents, i1, j1, i2, j2, self.lc, residual_mean, residual_std,
-                            as_int16=as_int16)
+        mean = self.residual_mean if residual_mean is None else residual_mean
+        std = self.residual_std if residual_std is None else residual_std
+        if mean is None or std is None:
+            raise ValueError("get_elev needs residual_mean / residual_std (constructor or call arguments)")
+        return compute_elev(self.residual, self.latents, i1, j1, i2, j2, self.lc, mean, std, as_int16=as_int16)
+
+    def get(self, i1: int, j1: int, i2: int, j2: int, with_climate: bool = False) -> dict:
+        """WorldPipeline.get (world_pipeline.py:1367-1384) for the part that is on the device: {'elev': fp32 [H, W] in
+        metres (a CUDA tensor; the reference returns CPU), 'climate': None}.  The climate read-out (_compute_climate,
+        :1314-1365: local lapse-rate regression + grid_sample of the coarse map) is not implemented yet."""
+        if with_climate:
+            raise NotImplementedError("TerrainPipeline.get: the climate read-out (world_pipeline.py:1314-1365) is not "
+                                      "implemented on the B200 path yet; call with with_climate=False")
+        return {"elev": self.get_elev(i1, j1, i2, j2), "climate": None}
 
     def residual_normalized(self, i1: int, j1: int, i2: int, j2: int) -> torch.Tensor:
         """Blended decoder output over pixel rows [i1,i2) x columns [j1,j2): residual[0] / residual[1]."""
