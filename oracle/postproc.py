@@ -6,6 +6,9 @@ What it restates (numpy float32, one function per reference function, cited by f
   * laplacian_decode / laplacian_encode / laplacian_denoise / resize_extrapolated / pad_linear_extrapolation
                                                      terrain_diffusion/data/laplacian_encoder.py:6-137
   * _elev_to_int16                                   terrain_diffusion/inference/api.py:73-77
+  * WorldPipeline._compute_climate                   terrain_diffusion/inference/world_pipeline.py:1314-1365
+  * local_baseline_temperature_torch                 terrain_diffusion/inference/postprocessing.py:262-326
+    (+ torch's avg_pool2d and grid_sample(bilinear, border, align_corners=False) as they are used there)
 and the two third-party pieces those call (not under /root/reference; torchvision 0.26 / torch 2.11 are installed here,
 so the restatement is pinned against the reference run through them -- tests/golden/make_golden_post.py):
   * torchvision.transforms.functional.resize(tensor, size, BILINEAR) -> torch interpolate(mode="bilinear",
@@ -168,3 +171,88 @@ def compute_elev(i1, j1, i2, j2, residual_planes, latents_planes, scale, residua
 def elev_to_int16(elev: np.ndarray) -> np.ndarray:
     """api.py:73-77."""
     return np.clip(np.floor(elev.astype(F32)), -32768, 32767).astype("<i2")
+
+
+# ---------------------------------------------------------------------------------------------------- climate read-out
+# (groundwork for the device version: restated and pinned, not yet on the GPU path)
+def _avg_pool_valid(x: np.ndarray, win: int) -> np.ndarray:
+    """F.avg_pool2d(x, win, stride=1, padding=0) on [H, W] (float32 window sum in row-major tap order, / win^2)."""
+    h, w = x.shape
+    oh, ow = h - win + 1, w - win + 1
+    acc = np.zeros((oh, ow), F32)
+    for dy in range(win):
+        for dx in range(win):
+            acc = (acc + x[dy:dy + oh, dx:dx + ow]).astype(F32)
+    return (acc / F32(win * win)).astype(F32)
+
+
+def local_baseline_temperature(T: np.ndarray, e: np.ndarray, win: int, beta_clip=(-0.012, 0.0), fallback_beta=-0.0065,
+                               eps=1e-6, fallback_threshold=0.3):
+    """inference/postprocessing.py:262-326: land-weighted windowed regression of temperature on elevation."""
+    T, e = T.astype(F32), e.astype(F32)
+    wmask = (e > 0).astype(F32)
+    den = _avg_pool_valid(wmask, win)
+
+    def wavg(x):
+        return (_avg_pool_valid((x * wmask).astype(F32), win) / (den + F32(eps))).astype(F32)
+
+    mu_T, mu_e, mu_e2, mu_eT = wavg(T), wavg(e), wavg((e * e).astype(F32)), wavg((e * T).astype(F32))
+    var_e = (mu_e2 - mu_e ** 2).astype(F32)
+    cov_eT = (mu_eT - mu_e * mu_T).astype(F32)
+    beta = (cov_eT / (var_e + F32(eps))).astype(F32)
+    invalid = (var_e < 1.0) | (den < fallback_threshold)
+    beta = np.where(invalid, F32(fallback_beta), beta).astype(F32)
+    beta = np.clip(beta, F32(beta_clip[0]), F32(beta_clip[1])).astype(F32)
+    pad = (win - 1) // 2
+    T_sea = (T[pad:-pad, pad:-pad] - beta * e[pad:-pad, pad:-pad]).astype(F32)
+    return T_sea, beta
+
+
+def _grid_sample_border(features: np.ndarray, gy: np.ndarray, gx: np.ndarray) -> np.ndarray:
+    """F.grid_sample(features[None], grid, mode='bilinear', padding_mode='border', align_corners=False) on [C, H, W]
+    with normalised coordinates gy, gx [h, w] (float32 throughout, like ATen's grid sampler)."""
+    _, H, W = features.shape
+    def unnorm(g, size):
+        c = (((g + F32(1.0)) * F32(size)) - F32(1.0)) / F32(2.0)
+        return np.clip(c.astype(F32), F32(0.0), F32(size - 1)).astype(F32)
+    y, x = unnorm(gy.astype(F32), H), unnorm(gx.astype(F32), W)
+    y0, x0 = np.floor(y), np.floor(x)
+    wy1, wx1 = (y - y0).astype(F32), (x - x0).astype(F32)
+    wy0, wx0 = (F32(1.0) - wy1).astype(F32), (F32(1.0) - wx1).astype(F32)
+    y0i, x0i = y0.astype(np.int64), x0.astype(np.int64)
+    y1i, x1i = y0i + 1, x0i + 1
+    def tap(yi, xi, wgt):
+        ok = (yi >= 0) & (yi < H) & (xi >= 0) & (xi < W)
+        v = features[:, np.clip(yi, 0, H - 1), np.clip(xi, 0, W - 1)]
+        return np.where(ok[None], v * wgt[None], F32(0.0)).astype(F32)
+    out = tap(y0i, x0i, (wy0 * wx0).astype(F32))
+    out = (out + tap(y0i, x1i, (wy0 * wx1).astype(F32))).astype(F32)
+    out = (out + tap(y1i, x0i, (wy1 * wx0).astype(F32))).astype(F32)
+    return (out + tap(y1i, x1i, (wy1 * wx1).astype(F32))).astype(F32)
+
+
+def compute_climate(i1, j1, i2, j2, elev: np.ndarray, coarse_planes, scale: int):
+    """world_pipeline.py:1314-1365: [temperature (lapse-rate corrected), coarse ch 3, 4, 5, lapse rate] x [H, W].
+    coarse_planes(a, b, c, d) -> [C+1, b-a, d-c] un-normalised planes of the coarse canvas (1/(32*scale) resolution)."""
+    S = 32 * scale
+    ci1, cj1 = i1 // S, j1 // S
+    ci2, cj2 = -((-i2) // S), -((-j2) // S)
+    win = 15
+    cpad = (win - 1) // 2 + 1
+    c = coarse_planes(ci1 - cpad, ci2 + cpad, cj1 - cpad, cj2 + cpad).astype(F32)
+    cmap = (c[:-1] / c[-1:]).astype(F32)
+    e0 = np.maximum(F32(0.0), cmap[0])
+    coarse_elev = (np.sign(cmap[0]) * np.square(e0)).astype(F32)
+    t_base, beta = local_baseline_temperature(cmap[2], coarse_elev, win=win, fallback_threshold=0.02)
+    central = cmap[:, win // 2:-(win // 2), win // 2:-(win // 2)]
+    Hs, Ws = t_base.shape
+    ii = np.arange(i1, i2, dtype=np.int64)[:, None] + np.zeros((1, j2 - j1), np.int64)
+    jj = np.arange(j1, j2, dtype=np.int64)[None, :] + np.zeros((i2 - i1, 1), np.int64)
+    u = (((ii.astype(F32) + F32(0.5)) / F32(S)) - F32(ci1) + F32(0.5)).astype(F32)
+    v = (((jj.astype(F32) + F32(0.5)) / F32(S)) - F32(cj1) + F32(0.5)).astype(F32)
+    gy = (((u + F32(0.5)) * F32(2.0)) / F32(Hs) - F32(1.0)).astype(F32)
+    gx = (((v + F32(0.5)) * F32(2.0)) / F32(Ws) - F32(1.0)).astype(F32)
+    feats = np.concatenate([t_base[None], beta[None], central], axis=0).astype(F32)
+    up = _grid_sample_border(feats, gy, gx)
+    t_real = (up[0] + up[1] * np.maximum(elev.astype(F32), F32(0.0))).astype(F32)
+    return np.stack([t_real, up[2 + 3], up[2 + 4], up[2 + 5], up[1]]).astype(F32)

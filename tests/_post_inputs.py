@@ -49,3 +49,11 @@ def elev_canvases():
     resid = FakeCanvas(1000, 1, (-160, -200), (480, 560), 0.0, 0.8)
     lat = FakeCanvas(2000, 5, (-20, -25), (60, 70), 0.2, 0.6)
     return resid, lat
+
+
+def coarse_canvas():
+    """Coarse canvas at 1/256 resolution: 6 value planes (0 = signed-sqrt elevation, 2 = temperature, ...) + weight."""
+    c = FakeCanvas(3000, 6, (-12, -12), (30, 32), 0.0, 1.0)
+    c.val[0] = field(3100, 30, 32, 5.0, 18.0)        # signed sqrt of metres: mostly land, some ocean (< 0)
+    c.val[2] = field(3200, 30, 32, 12.0, 6.0)        # temperature, deg C
+    return c

@@ -23,7 +23,8 @@ sys.path[:0] = [str(ROOT / "oracle" / "_stub"), str(REF), str(ROOT)]
 
 from terrain_diffusion.data.laplacian_encoder import laplacian_decode, laplacian_denoise  # noqa: E402
 
-from tests._post_inputs import (ELEV_WINDOWS, RESIDUAL_MEAN, RESIDUAL_STD, elev_canvases, laplacian_case)  # noqa: E402
+from tests._post_inputs import (ELEV_WINDOWS, RESIDUAL_MEAN, RESIDUAL_STD, coarse_canvas, elev_canvases,  # noqa: E402
+                                laplacian_case)
 
 torch.set_grad_enabled(False)
 
@@ -51,16 +52,25 @@ def main():
     body = []
     for n in tree.body:
         if isinstance(n, ast.ClassDef) and n.name == "WorldPipeline":
-            body += [m for m in n.body if isinstance(m, ast.FunctionDef) and m.name == "_compute_elev"]
-    assert body, "WorldPipeline._compute_elev not found"
-    ns = {"torch": torch, "np": np, "laplacian_denoise": laplacian_denoise, "laplacian_decode": laplacian_decode}
+            body += [m for m in n.body if isinstance(m, ast.FunctionDef) and m.name in ("_compute_elev", "_compute_climate")]
+    assert len(body) == 2, "WorldPipeline._compute_elev / _compute_climate not found"
+    # local_baseline_temperature_torch lives in inference/postprocessing.py, which imports matplotlib (absent here):
+    # the function definition alone is extracted the same way
+    pp = ast.parse((REF / "terrain_diffusion/inference/postprocessing.py").read_text())
+    body += [n for n in pp.body if isinstance(n, ast.FunctionDef) and n.name == "local_baseline_temperature_torch"]
+    assert len(body) == 3
+    import torch.nn.functional as F
+    ns = {"torch": torch, "np": np, "F": F, "laplacian_denoise": laplacian_denoise, "laplacian_decode": laplacian_decode}
     exec(compile(ast.Module(body=body, type_ignores=[]), "world_pipeline_extract", "exec"), ns)
     resid, lat = elev_canvases()
-    fake = SimpleNamespace(kwargs={"residual_mean": RESIDUAL_MEAN, "residual_std": RESIDUAL_STD}, latents=TorchCanvas(lat))
+    fake = SimpleNamespace(kwargs={"residual_mean": RESIDUAL_MEAN, "residual_std": RESIDUAL_STD}, latents=TorchCanvas(lat),
+                           coarse=TorchCanvas(coarse_canvas()))
     for name, (i1, j1, i2, j2) in ELEV_WINDOWS.items():
         elev = ns["_compute_elev"](fake, i1, j1, i2, j2, TorchCanvas(resid), 8)
         out[f"elev_{name}"] = elev.numpy()
-        print(name, tuple(elev.shape), float(elev.abs().max()))
+        clim = ns["_compute_climate"](fake, i1, j1, i2, j2, elev, 8)
+        out[f"climate_{name}"] = clim.numpy()[:, ::2, ::2]        # every other pixel: keeps the fixture small
+        print(name, tuple(elev.shape), float(elev.abs().max()), tuple(clim.shape), [round(float(c.mean()), 4) for c in clim])
     np.savez_compressed(HERE / "post_golden.npz", **out)
     print("wrote", HERE / "post_golden.npz", sum(v.nbytes for v in out.values()) // 1024, "KiB raw")
 

@@ -7,7 +7,8 @@ import numpy as np
 import pytest
 
 from oracle import postproc as P
-from tests._post_inputs import (ELEV_WINDOWS, RESIDUAL_MEAN, RESIDUAL_STD, elev_canvases, laplacian_case)
+from tests._post_inputs import (ELEV_WINDOWS, RESIDUAL_MEAN, RESIDUAL_STD, coarse_canvas, elev_canvases,
+                                laplacian_case)
 
 G = np.load(Path(__file__).resolve().parent / "golden" / "post_golden.npz")
 
@@ -66,3 +67,16 @@ def test_read_out_refuses_cpu_tensors():
         H.resize_bilinear(torch.zeros(8, 8), (16, 16))
     with pytest.raises(L.TdxError):
         H.gaussian_blur(torch.zeros(16, 16), 11, 5.0)
+
+
+@pytest.mark.parametrize("name", list(ELEV_WINDOWS))
+def test_oracle_compute_climate_matches_reference_golden(name):
+    """Groundwork for the device version of WorldPipeline._compute_climate (world_pipeline.py:1314-1365): the restated
+    lapse-rate regression + border-clamped bilinear grid_sample agree with the reference on all five output channels."""
+    i1, j1, i2, j2 = ELEV_WINDOWS[name]
+    c = P.compute_climate(i1, j1, i2, j2, G[f"elev_{name}"], coarse_canvas().planes, 8)
+    g = G[f"climate_{name}"]                               # stored at every other pixel
+    assert c.shape == (5, i2 - i1, j2 - j1)
+    for k in range(5):
+        assert rel(c[k, ::2, ::2], g[k]) < 2e-6, k
+    assert float(c[4].min()) >= -0.012 - 1e-9 and float(c[4].max()) <= 1e-9   # lapse rate stays inside beta_clip
