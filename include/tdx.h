@@ -224,6 +224,21 @@ int tdx_gaussian_blur(const float* x, int32_t h, int32_t w, float* out, int32_t 
 int tdx_post_combine(const float* a, int64_t a_pitch, const float* b, int64_t b_pitch, float* out, int16_t* out_i16,
                      int32_t h, int32_t w, int32_t signed_square, void* stream);
 
+/* Climate read-out (WorldPipeline._compute_climate, inference/world_pipeline.py:1314-1365).
+ * tdx_lapse_rate = local_baseline_temperature_torch (inference/postprocessing.py:262-326) on the normalised coarse
+ * planes: `coarse_elev_sqrt` is coarse channel 0 (signed square root of metres; e = max(0, c)^2 inside), `temp` channel
+ * 2; outputs are the (h-win+1) x (w-win+1) valid-window maps of sea-level temperature and lapse rate. */
+int tdx_lapse_rate(const float* temp, const float* coarse_elev_sqrt, int32_t h, int32_t w, int32_t win, float beta_lo,
+                   float beta_hi, float fallback_beta, float eps, float fallback_threshold, float* t_sea, float* beta,
+                   void* stream);
+/* Bilinear, border-clamped grid_sample (align_corners=False) of [t_sea, beta, coarse channels 3..5] at the centres of
+ * pixels [i1, i1+h) x [j1, j1+w) (one coarse cell = coarse_stride pixels, window origin cell (ci1, cj1); the sampled
+ * part of `coarse` [n_ch][hc][wc] starts at (crop, crop) and has the size of t_sea) and the lapse-rate correction:
+ * out[5][h][w] = {t_sea + beta*max(elev, 0), coarse 3, coarse 4, coarse 5, beta}. */
+int tdx_climate_sample(const float* t_sea, const float* beta, const float* coarse, int32_t n_ch, int32_t hc, int32_t wc,
+                       int32_t crop, const float* elev, int32_t i1, int32_t j1, int32_t h, int32_t w,
+                       int32_t coarse_stride, int32_t ci1, int32_t cj1, float* out, void* stream);
+
 /* Tile-seeded N(0,1) field, bit-exact with inference/portable_rng.py + world_pipeline.py:66-115 */
 int tdx_noise_patch(uint64_t base_seed, int64_t y0, int64_t x0, int32_t h, int32_t w, int32_t channels,
                     int32_t tile_h, int32_t tile_w, float* out, void* workspace, int64_t workspace_bytes,

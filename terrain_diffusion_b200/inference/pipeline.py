@@ -3,8 +3,7 @@ exactly like WorldPipeline._build_coarse_stage / _build_latent_stage / _build_de
 (reference inference/world_pipeline.py:961-992, 1133-1203, 1244-1270), with every stage on the GPU.
 
 What is NOT here (out of the hot-path scope): the Perlin/WorldClim conditioning synthesis (pass a
-`conditioning_fn(i1, i2, j1, j2) -> [5, h, w]`), climate post-processing (lapse rates; the elevation read-out IS here:
-`get_elev`), HDF5
+`conditioning_fn(i1, i2, j1, j2) -> [5, h, w]`), HDF5
 tile stores, the CLI / HTTP front-ends.  Window geometry, seeds, phase times and batching follow the reference.
 """
 from __future__ import annotations
@@ -97,14 +96,13 @@ class TerrainPipeline:
             raise ValueError("get_elev needs residual_mean / residual_std (constructor or call arguments)")
         return compute_elev(self.residual, self.latents, i1, j1, i2, j2, self.lc, mean, std, as_int16=as_int16)
 
-    def get(self, i1: int, j1: int, i2: int, j2: int, with_climate: bool = False) -> dict:
-        """WorldPipeline.get (world_pipeline.py:1367-1384) for the part that is on the device: {'elev': fp32 [H, W] in
-        metres (a CUDA tensor; the reference returns CPU), 'climate': None}.  The climate read-out (_compute_climate,
-        :1314-1365: local lapse-rate regression + grid_sample of the coarse map) is not implemented yet."""
-        if with_climate:
-            raise NotImplementedError("TerrainPipeline.get: the climate read-out (world_pipeline.py:1314-1365) is not "
-                                      "implemented on the B200 path yet; call with with_climate=False")
-        return {"elev": self.get_elev(i1, j1, i2, j2), "climate": None}
+    def get(self, i1: int, j1: int, i2: int, j2: int, with_climate: bool = True) -> dict:
+        """WorldPipeline.get (world_pipeline.py:1367-1384), computed on the device: {'elev': fp32 [H, W] in metres,
+        'climate': fp32 [5, H, W] or None} -- CUDA tensors (the reference returns CPU tensors; call .cpu() to match)."""
+        from .postproc import compute_climate
+        elev = self.get_elev(i1, j1, i2, j2)
+        climate = compute_climate(self.coarse, i1, j1, i2, j2, elev, self.lc) if with_climate else None
+        return {"elev": elev, "climate": climate}
 
     def residual_normalized(self, i1: int, j1: int, i2: int, j2: int) -> torch.Tensor:
         """Blended decoder output over pixel rows [i1,i2) x columns [j1,j2): residual[0] / residual[1]."""

@@ -151,3 +151,39 @@ def compute_elev(residual_canvas, latents_canvas, i1: int, j1: int, i2: int, j2:
     oi, oj = i1 - pi1, j1 - pj1
     h, w = i2 - i1, j2 - j1
     return _combine(residual_p[oi:oi + h, oj:oj + w], up[oi:oi + h, oj:oj + w], signed_square=True, int16=as_int16)
+
+
+def compute_climate(coarse_canvas, i1: int, j1: int, i2: int, j2: int, elev: torch.Tensor, scale: int) -> torch.Tensor:
+    """Climate over pixel rows [i1, i2) x columns [j1, j2) (WorldPipeline._compute_climate, world_pipeline.py:1314-1365):
+    fp32 CUDA [5, H, W] = {temperature with the local lapse-rate correction, coarse channels 3, 4, 5, lapse rate}.
+
+    `coarse_canvas[:, a:b, c:d]` returns the un-normalised planes of the coarse canvas (one cell = 32*scale pixels; channel
+    0 = signed-sqrt elevation, 2 = temperature, last = weight); `elev` is compute_elev's result for the same window."""
+    elev = _chk(elev, "compute_climate(elev)")
+    if tuple(elev.shape) != (i2 - i1, j2 - j1):
+        raise ValueError(f"elev is {tuple(elev.shape)}, the window is {(i2 - i1, j2 - j1)}")
+    S = 32 * scale
+    ci1, cj1 = i1 // S, j1 // S
+    ci2, cj2 = -((-i2) // S), -((-j2) // S)
+    win = 15                                           # coarse_window_size (world_pipeline.py:1324)
+    cpad = (win - 1) // 2 + 1
+    c = coarse_canvas[:, ci1 - cpad:ci2 + cpad, cj1 - cpad:cj2 + cpad]
+    if not c.is_cuda:
+        raise L.TdxError("compute_climate: the coarse canvas must return CUDA tensors (no CPU path)")
+    c = c.float().contiguous()
+    nch, hc, wc = c.shape[0] - 1, c.shape[1], c.shape[2]
+    s = L.current_stream_ptr()
+    cmap = torch.empty((nch, hc, wc), dtype=torch.float32, device=c.device)
+    for k in range(nch):                               # coarse_map = coarse_init[:-1] / coarse_init[-1:]
+        L.check(L.lib().tdx_post_normalize(_p(c[k]), _p(c[-1]), wc, _p(cmap[k]), hc, wc, 1.0, 0.0, s))
+    hs, ws = hc - win + 1, wc - win + 1
+    t_sea = torch.empty((hs, ws), dtype=torch.float32, device=c.device)
+    beta = torch.empty((hs, ws), dtype=torch.float32, device=c.device)
+    # local_baseline_temperature_torch(coarse_map[2], coarse_elev_denorm, win=15, fallback_threshold=0.02), defaults of
+    # inference/postprocessing.py:262-270 otherwise
+    L.check(L.lib().tdx_lapse_rate(_p(cmap[2]), _p(cmap[0]), hc, wc, win, -0.012, 0.0, -0.0065, 1e-6, 0.02, _p(t_sea),
+                                   _p(beta), s))
+    out = torch.empty((5, i2 - i1, j2 - j1), dtype=torch.float32, device=c.device)
+    L.check(L.lib().tdx_climate_sample(_p(t_sea), _p(beta), _p(cmap), nch, hc, wc, win // 2, _p(elev), i1, j1, i2 - i1,
+                                       j2 - j1, S, ci1, cj1, _p(out), s))
+    return out

@@ -13,7 +13,8 @@ import torch
 from oracle import postproc as P
 from terrain_diffusion_b200 import _lib as L
 from terrain_diffusion_b200.inference import postproc as H
-from tests._post_inputs import (ELEV_WINDOWS, RESIDUAL_MEAN, RESIDUAL_STD, elev_canvases, field, laplacian_case)
+from tests._post_inputs import (ELEV_WINDOWS, RESIDUAL_MEAN, RESIDUAL_STD, coarse_canvas, elev_canvases, field,
+                                laplacian_case)
 
 pytestmark = pytest.mark.gpu
 G = np.load(Path(__file__).resolve().parent / "golden" / "post_golden.npz")
@@ -88,3 +89,20 @@ def test_compute_elev_matches_reference_golden_and_packs_int16(name):
     assert torch.equal(only, elev)
     with pytest.raises(ValueError):
         H.compute_elev(CudaCanvas(resid), CudaCanvas(lat), i2, j1, i1, j2, 8, RESIDUAL_MEAN, RESIDUAL_STD)
+
+
+@pytest.mark.parametrize("name", list(ELEV_WINDOWS))
+def test_compute_climate_matches_reference_golden(name):
+    """tdx_lapse_rate + tdx_climate_sample = WorldPipeline._compute_climate (world_pipeline.py:1314-1365)."""
+    i1, j1, i2, j2 = ELEV_WINDOWS[name]
+    cc = coarse_canvas()
+    elev = G[f"elev_{name}"]
+    got = H.compute_climate(CudaCanvas(cc), i1, j1, i2, j2, dev(elev), 8).cpu().numpy()
+    ref = P.compute_climate(i1, j1, i2, j2, elev, cc.planes, 8)
+    g = G[f"climate_{name}"]                               # reference, stored at every other pixel
+    assert got.shape == ref.shape == (5, i2 - i1, j2 - j1)
+    for k in range(5):
+        assert rel(got[k], ref[k]) < 2e-6, k
+        assert rel(got[k, ::2, ::2], g[k]) < 1e-5, k
+    with pytest.raises(ValueError):
+        H.compute_climate(CudaCanvas(cc), i1, j1, i2 + 1, j2, dev(elev), 8)
