@@ -80,3 +80,34 @@ def test_oracle_compute_climate_matches_reference_golden(name):
     for k in range(5):
         assert rel(c[k, ::2, ::2], g[k]) < 2e-6, k
     assert float(c[4].min()) >= -0.012 - 1e-9 and float(c[4].max()) <= 1e-9   # lapse rate stays inside beta_clip
+
+
+def test_pipeline_get_wires_the_read_out_like_the_reference(monkeypatch):
+    """TerrainPipeline.get / get_elev (WorldPipeline.get, world_pipeline.py:1367-1384): canvases, compression factor and
+    the residual statistics reach compute_elev / compute_climate; missing statistics and empty windows are errors."""
+    from terrain_diffusion_b200.inference import postproc as H
+    from terrain_diffusion_b200.inference.pipeline import TerrainPipeline
+    calls = {}
+
+    def fake_elev(resid, lat, i1, j1, i2, j2, scale, mean, std, sigma=5, as_int16=False):
+        calls["elev"] = (resid, lat, i1, j1, i2, j2, scale, mean, std, as_int16)
+        return "ELEV16" if as_int16 else "ELEV"
+
+    def fake_climate(coarse, i1, j1, i2, j2, elev, scale):
+        calls["climate"] = (coarse, i1, j1, i2, j2, elev, scale)
+        return "CLIMATE"
+
+    monkeypatch.setattr(H, "compute_elev", fake_elev)
+    monkeypatch.setattr(H, "compute_climate", fake_climate)
+    p = object.__new__(TerrainPipeline)
+    p.residual, p.latents, p.coarse, p.lc = "R", "L", "C", 8
+    p.residual_mean, p.residual_std = None, None
+    with pytest.raises(ValueError):
+        p.get_elev(0, 0, 8, 8)
+    p.residual_mean, p.residual_std = 0.5, 2.0
+    assert p.get(-3, 4, 61, 132) == {"elev": "ELEV", "climate": "CLIMATE"}
+    assert calls["elev"] == ("R", "L", -3, 4, 61, 132, 8, 0.5, 2.0, False)
+    assert calls["climate"] == ("C", -3, 4, 61, 132, "ELEV", 8)
+    assert p.get(0, 0, 8, 8, with_climate=False) == {"elev": "ELEV", "climate": None}
+    assert p.get_elev(0, 0, 8, 8, residual_mean=1.0, residual_std=3.0, as_int16=True) == "ELEV16"
+    assert calls["elev"][7:] == (1.0, 3.0, True)
