@@ -14,6 +14,25 @@ def tile_seed(base_seed: int, ty: int, tx: int) -> int:
     return int(L.lib().tdx_tile_seed(int(base_seed) & MASK64, int(ty), int(tx)))
 
 
+def next_seed(seed: int | None) -> int:
+    """Derive a new 64-bit seed from a parent seed, or from the clock when seed is None / 0 (portable_rng.py:31-42):
+    two PCG-XSH-RR 64/32 outputs, low word first.  Host integer arithmetic (a seed is drawn once per world)."""
+    state = (int(seed) & MASK64) if seed is not None else 0
+    if state == 0:
+        import time
+        state = int(time.perf_counter_ns()) & MASK64
+
+    def step(st):
+        st = (st * 6364136223846793005 + 1442695040888963407) & MASK64
+        x = (((st >> 18) ^ st) >> 27) & 0xFFFFFFFF
+        rot = st >> 59
+        return st, ((x >> rot) | (x << ((32 - rot) & 31))) & 0xFFFFFFFF
+
+    state, lo = step(state)
+    state, hi = step(state)
+    return int(((hi << 32) | lo) & MASK64)
+
+
 _workspaces: dict = {}
 
 

@@ -22,9 +22,11 @@ class TerrainPipeline:
     def __init__(self, coarse_model, base_model, decoder_model, seed: int, conditioning_fn, *, coarse_means, coarse_stds,
                  cond_snr, histogram_raw, latents_means, latents_stds, latents_batch_size: int = 16,
                  decoder_tile_size: int = 512, decoder_tile_stride: int = 384, latent_compression: int = 8,
-                 t_inter: float | None = None, residual_mean: float | None = None, residual_std: float | None = None):
+                 t_inter: float | None = None, residual_mean: float | None = None, residual_std: float | None = None,
+                 native_resolution: float = 90.0):
         self.device = decoder_model.device
-        self.seed = int(seed)
+        self.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        self.native_resolution = native_resolution          # metres per pixel (world_pipeline.py:293,331)
         self.coarse_model, self.base_model, self.decoder_model = coarse_model, base_model, decoder_model
         self.conditioning_fn = conditioning_fn
         self.kw = dict(coarse_means=coarse_means, coarse_stds=coarse_stds)
@@ -41,15 +43,14 @@ class TerrainPipeline:
 
         # ---- coarse: 64^2 tiles, stride 48, 20-step DPM-Solver++ (world_pipeline.py:961-992)
         ww64 = linear_weight_window(64, dev)
-        t_cond = torch.atan(self.cond_snr)
-        cond_inputs = [v.view(-1) for v in torch.log(torch.tan(t_cond) / 8.0)]
+        self._set_cond(self.cond_snr)
         coarse_sched = EDMDPMSolverMultistepScheduler(sigma_min=0.002, sigma_max=80, sigma_data=0.5)
 
         def f_coarse(ctx):
             _, i, j = ctx
             smap = self.conditioning_fn(i * 48, i * 48 + 64, j * 48, j * 48 + 64)
-            return coarse_stage_tile(self.coarse_model, coarse_sched, self.seed, ctx, smap, t_cond, cond_inputs, ww64,
-                                     coarse_means, coarse_stds)
+            return coarse_stage_tile(self.coarse_model, coarse_sched, self.seed, ctx, smap, self._t_cond,
+                                     self._cond_inputs, ww64, coarse_means, coarse_stds)
 
         self.coarse = LazyCanvas(7, f_coarse, TensorWindow((7, 64, 64), (7, 48, 48)), dev)
 
@@ -82,6 +83,47 @@ class TerrainPipeline:
         self.residual = LazyCanvas(2, f_dec, TensorWindow((2, T, T), (2, S, S)), dev, args=(self.latents,),
                                    args_windows=(TensorWindow((6, T // self.lc, T // self.lc),
                                                               (6, S // self.lc, S // self.lc)),))
+
+    # ------------------------------------------------------------------ small WorldPipeline API (host state only)
+    def _set_cond(self, cond_snr) -> None:
+        self.cond_snr = torch.as_tensor(cond_snr, dtype=torch.float32)
+        self._t_cond = torch.atan(self.cond_snr)
+        self._cond_inputs = [v.view(-1) for v in torch.log(torch.tan(self._t_cond) / 8.0)]
+
+    def empty_cache(self) -> None:
+        """Drop every cached window of every stage (WorldPipeline.empty_cache, world_pipeline.py:697-704)."""
+        for canvas in (self.coarse, self.latents_init, self.latents, self.residual):
+            canvas.clear_cache()
+
+    def change_seed(self, seed: int | None = None) -> bool:
+        """New world seed (masked to 64 bits; None draws one like portable_rng.next_seed(None)) and all cached tiles
+        dropped; False (no-op) when the seed is unchanged (world_pipeline.py:743-763).  A seed-dependent
+        `conditioning_fn` must read `pipeline.seed` itself -- the conditioning synthesis is the caller's."""
+        from .noise import next_seed
+        new_seed = (int(seed) & 0xFFFFFFFFFFFFFFFF) if seed is not None else next_seed(None)
+        if new_seed == self.seed:
+            return False
+        self.seed = new_seed
+        self.empty_cache()
+        return True
+
+    def set_cond_snr(self, cond_snr) -> None:
+        """Per-channel conditioning SNR (exactly five values) and a rebuild (world_pipeline.py:765-779)."""
+        if len(cond_snr) != 5:
+            raise ValueError("cond_snr must contain exactly 5 values.")
+        self._set_cond([float(x) for x in cond_snr])
+        self.empty_cache()
+
+    def close(self) -> None:
+        """Release the cached tiles (the reference also closes its HDF5 tile store here, world_pipeline.py:706-712)."""
+        self.empty_cache()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, exc_type, exc_val, exc_tb):
+        self.close()
+        return False
 
     def get_elev(self, i1: int, j1: int, i2: int, j2: int, residual_mean: float | None = None,
                  residual_std: float | None = None, as_int16: bool = False):

@@ -111,3 +111,51 @@ def test_pipeline_get_wires_the_read_out_like_the_reference(monkeypatch):
     assert p.get(0, 0, 8, 8, with_climate=False) == {"elev": "ELEV", "climate": None}
     assert p.get_elev(0, 0, 8, 8, residual_mean=1.0, residual_std=3.0, as_int16=True) == "ELEV16"
     assert calls["elev"][7:] == (1.0, 3.0, True)
+
+
+def test_pipeline_small_api_mirrors_world_pipeline(monkeypatch):
+    """seed / change_seed / set_cond_snr / empty_cache / context manager / native_resolution (world_pipeline.py:293,331,
+    690-712,743-779).  The canvases and stage kernels are replaced by recorders so the constructor runs without a GPU."""
+    import torch
+    from types import SimpleNamespace
+
+    from terrain_diffusion_b200.inference import pipeline as PL
+    from terrain_diffusion_b200.inference.noise import next_seed
+
+    class RecCanvas:
+        def __init__(self, channels, f, win, dev, args=(), args_windows=(), batch_size=None):
+            self.f, self.done = f, set()
+
+        def clear_cache(self):
+            self.done.clear()
+
+    seen = {}
+    monkeypatch.setattr(PL, "LazyCanvas", RecCanvas)
+    monkeypatch.setattr(PL, "linear_weight_window", lambda size, dev: torch.zeros(size, size))
+    monkeypatch.setattr(PL, "coarse_stage_tile", lambda *a: seen.setdefault("coarse", a))
+    dummy = SimpleNamespace(device=torch.device("cpu"))
+    p = PL.TerrainPipeline(dummy, dummy, dummy, 2 ** 64 + 7, lambda *a: "SMAP", coarse_means=[0.0] * 6,
+                           coarse_stds=[1.0] * 6, cond_snr=[0.5, 0.4, 0.3, 0.2, 0.1], histogram_raw=[0.0] * 5,
+                           latents_means=[0.0] * 5, latents_stds=[1.0] * 5, residual_mean=0.1, residual_std=1.2)
+    assert p.seed == 7 and p.native_resolution == 90.0
+    assert p.change_seed(7) is False and p.change_seed(2 ** 64 + 9) is True and p.seed == 9
+    p.coarse.done.add((0, 0))
+    p.residual.done.add((1, 2))
+    assert p.change_seed(None) is True and 0 <= p.seed < 2 ** 64 and not p.coarse.done and not p.residual.done
+    with pytest.raises(ValueError):
+        p.set_cond_snr([1.0, 2.0])
+    p.latents.done.add((0, 0))
+    p.set_cond_snr([1, 2, 3, 4, 5])
+    assert not p.latents.done and torch.allclose(p._t_cond, torch.atan(torch.tensor([1.0, 2, 3, 4, 5])))
+    assert len(p._cond_inputs) == 5 and abs(float(p._cond_inputs[0]) - float(np.log(1.0 / 8.0))) < 1e-6
+    # the coarse stage callback picks up the CURRENT seed and conditioning (world_pipeline.py:909-959)
+    p.coarse.f((0, 2, -1))
+    args = seen["coarse"]
+    assert args[2] == p.seed and args[3] == (0, 2, -1) and args[4] == "SMAP" and args[5] is p._t_cond
+    assert args[6] is p._cond_inputs
+    with p as q:
+        q.latents_init.done.add((3, 3))
+    assert not p.latents_init.done
+    # portable_rng.next_seed known answers (computed with the reference: parents 1, 42, 2^63+12345, 2^64-1)
+    assert [next_seed(s) for s in (1, 42, 2 ** 63 + 12345, 0xFFFFFFFFFFFFFFFF)] == [
+        14210067475669473140, 1039766031909981117, 1104045458667958325, 13583675427266712300]
