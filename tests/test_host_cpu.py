@@ -150,3 +150,30 @@ def test_first_convolution_weight_matrix_of_the_im2col_path_reproduces_the_3x3_c
     got = torch.einsum("ok,nkhw->nohw", w_mat[:, :9 * ci, 0, 0], cols)
     ref = F.conv2d(x, w_in, padding=1)
     assert torch.allclose(got, ref, atol=1e-5, rtol=1e-5)
+
+
+def test_new_entry_points_validate_their_arguments_without_a_gpu():
+    """im2col / read-out primitives reject bad descriptors before any CUDA call (return codes + tdx_last_error)."""
+    lib = L.lib()
+    d = L.TdxIm2colDesc()
+    assert lib.tdx_im2col_run(C.byref(d), None) != 0 and b"src[0]" in lib.tdx_last_error()
+    d.src[0] = 16
+    d.src_channels[0] = 3                       # 3 + ones = 4 input channels: not one of the shipped models
+    d.out = 16
+    d.k_pad = 64
+    d.n_img, d.height, d.width = 1, 8, 8
+    assert lib.tdx_im2col_run(C.byref(d), None) != 0 and b"input channels" in lib.tdx_last_error()
+    d.src_channels[0] = 5
+    d.k_pad = 128                               # 9 * 6 = 54 -> must be 64
+    assert lib.tdx_im2col_run(C.byref(d), None) != 0 and b"k_pad" in lib.tdx_last_error()
+    p = C.c_void_p(16)
+    assert lib.tdx_gaussian_blur(p, 16, 16, p, 11, 5.0, None) != 0 and b"aliased" in lib.tdx_last_error()
+    q = C.c_void_p(32)
+    assert lib.tdx_gaussian_blur(p, 16, 16, q, 10, 5.0, None) != 0 and b"kernel size" in lib.tdx_last_error()
+    assert lib.tdx_gaussian_blur(p, 5, 16, q, 11, 5.0, None) != 0 and b"reflect" in lib.tdx_last_error()
+    assert lib.tdx_resize_aa_axis(p, 8, 8, q, 16, 2, None) != 0 and b"axis" in lib.tdx_last_error()
+    assert lib.tdx_post_combine(p, 4, q, 8, q, None, 8, 8, 0, None) != 0      # pitch smaller than the width
+    assert lib.tdx_lapse_rate(p, q, 10, 20, 15, -0.012, 0.0, -0.0065, 1e-6, 0.02, q, q, None) != 0
+    assert b"window" in lib.tdx_last_error()
+    assert lib.tdx_climate_sample(p, p, p, 4, 20, 20, 7, p, 0, 0, 8, 8, 256, 0, 0, q, None) != 0
+    assert b"channels" in lib.tdx_last_error()
