@@ -76,7 +76,7 @@ typedef struct TdxIgemmDesc {
 } TdxIgemmDesc;
 
 /* Output channels per work item (64/128/192/256) the library prefers for this launch shape: balances the MMA issue
- * floor (max(86, N/2) cycles per K=16 step), L2->SM traffic and CTA count.  Pack the weights for this value. */
+ * pipe time (max(48, N/2) cycles per K=16 step), L2->SM traffic and CTA count.  Pack the weights for this value. */
 int tdx_igemm_choose_n(int32_t c_out, int32_t n_img, int32_t height, int32_t width, const int32_t* a_channels,
                        const int32_t* a_taps, int32_t n_seg);
 /* Elements of packed B for a descriptor's segments. */

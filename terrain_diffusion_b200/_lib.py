@@ -180,9 +180,22 @@ def check(rc: int) -> None:
         raise TdxError(f"libtdx error {rc}: {lib().tdx_last_error().decode()}")
 
 
-def current_stream_ptr() -> int:
+def current_stream_ptr(device=None) -> int:
     import torch
-    return torch.cuda.current_stream().cuda_stream
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def call(fn, device, *args) -> None:
+    """One libtdx launch on `device`: the device is made current for the call (libtdx launches on, and takes its
+    per-device scratch / SM count from, the CURRENT device -- it never calls cudaSetDevice itself) and the device's
+    current torch stream is appended as the last C argument.  A tensor that lives on cuda:1 while cuda:0 is current
+    would otherwise run on device 0 with device-1 pointers."""
+    import torch
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise TdxError(f"libtdx launch on a non-CUDA device ({device}); there is no CPU path")
+    with torch.cuda.device(device):
+        check(fn(*args, torch.cuda.current_stream(device).cuda_stream))
 
 
 def igemm_choose_n(c_out: int, n_img: int, height: int, width: int, segs) -> int:

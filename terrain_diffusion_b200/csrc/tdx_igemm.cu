@@ -191,6 +191,12 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
+// ---------------------------------------------------------------------------------------------- issue helpers
+// A value every lane already agrees on, moved into a UNIFORM register (REDUX writes its result there), so that
+// arithmetic on it stays on the uniform datapath and instructions with uniform operands (UTCHMMA) need no R2UR.
+__device__ __forceinline__ uint32_t uni(uint32_t v) { return __reduce_or_sync(0xffffffffu, v); }
+__device__ __forceinline__ uint64_t pack_desc(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
+
 // ---------------------------------------------------------------------------------------------- epilogue helpers
 __device__ __forceinline__ void load_acc(uint32_t taddr, float (&v)[kChunk]) {
   uint32_t r[kChunk];
@@ -269,7 +275,10 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CU
   float* stot = rss + 512;                                            // [128] per-pixel totals over the cluster
   float* xstat = stot + 128;                                          // [2 parity][kMaxSplit][128] from peer CTAs
 
-  const int warp = threadIdx.x >> 5;   // warp-uniform role id
+  // The role id goes through a shuffle so that ptxas KNOWS it is warp-uniform: with a plain threadIdx.x >> 5 the role
+  // branches count as divergent regions (code follows them), and inside a divergent region nothing is kept in uniform
+  // registers -- every UTCHMMA / TMA / mbarrier operand then costs an R2UR.
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
   if (p.trace && blockIdx.x == 0 && threadIdx.x == 0) p.trace[126] = clock64();
   if (p.timeline && threadIdx.x == 0) {
@@ -372,91 +381,100 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CU
     if (p.ksplit > 1) cluster_sync_all();
   } else if (warp == 2) {
     // ------------------------------------------------------------------ MMA issuer (one elected lane issues)
-    const uint32_t idesc = make_idesc_bf16(128, p.ncta);
+    // Everything a UTCHMMA reads (two 64-bit matrix descriptors, the TMEM address, the instruction descriptor) lives
+    // in UNIFORM registers.  ptxas only keeps a value there when it can prove it warp-uniform, and a value that
+    // passed through a per-thread register (shared-memory loads, the ring counters of a loop with a spin-wait in it)
+    // costs an R2UR per use: the round-1 loop spent ~70-86 cycles of issue per MMA on R2UR / uniform-register spills,
+    // while the tensor pipe needs 48 (N=64), 64 (N=128), 96 (N=192), 128 (N=256) cycles (tools/probe/mma_probe3.cu).
+    // So every loop-carried quantity below is seeded from a warp reduction (REDUX writes a uniform register) and only
+    // updated with uniform arithmetic; descriptors are (constant upper word, low word = base + compile-time offset).
+    const uint32_t idesc = uni(make_idesc_bf16(128, p.ncta));
     const uint32_t b_lbo = p.ncta * 16;
     const uint32_t a_sbo = (p.dbg & 1) ? 128 : kPatchW * 16;
-    // Descriptors are built as (constant upper bits) | (start address >> 4); per MMA only the 14-bit address field
-    // changes, by compile-time offsets for the tap (r*10 + c pixels) and the K step (2 planes of 2880 B), so the issue
-    // loop has no dependent address arithmetic between UTCHMMAs.
     const uint64_t a_hi = make_smem_desc(0, kKcBytes, a_sbo);
     const uint64_t b_hi = make_smem_desc(0, b_lbo, 128);
+    const uint32_t a_h = uni((uint32_t)(a_hi >> 32)), b_h = uni((uint32_t)(b_hi >> 32));
     // (in a cluster launch the shared-window address carries the CTA rank in its upper bits: keep the 14-bit field only)
-    const uint32_t a_ring16 = (smem_u32(a_ring) >> 4) & 0x3FFF, b_ring16 = (smem_u32(b_ring) >> 4) & 0x3FFF;
-    const uint32_t b_stage16 = p.b_stage_bytes >> 4, b_kstep16 = (2 * b_lbo) >> 4;
+    const uint32_t a_lo0 = uni((uint32_t)a_hi + ((smem_u32(a_ring) >> 4) & 0x3FFF));
+    const uint32_t b_lo0 = uni((uint32_t)b_hi + ((smem_u32(b_ring) >> 4) & 0x3FFF));
+    const uint32_t b_stage16 = uni((uint32_t)p.b_stage_bytes >> 4), b_kstep16 = uni((2 * b_lbo) >> 4);
     constexpr uint32_t a_kstep16 = (2 * kKcBytes) >> 4;
-    int sa = 0, sb = 0;
+    const uint32_t tmem_u = uni(tmem_base);
+    const uint32_t SBu = uni((uint32_t)p.SB);
+    const uint32_t resident = uni((uint32_t)p.resident);
+    uint32_t sa = uni(0), sb = uni(0);
     uint32_t pha = 0, phb = 0;
-    int it = 0;
+    uint32_t it = uni(0);
     int s0, s1;
     {
       const uint32_t bk = fdiv(blockIdx.x, p.fd_ks);
       stage_range(p, (int)(blockIdx.x - bk * p.fd_ks.d), s0, s1);
+      s0 = (int)uni((uint32_t)s0);
+      s1 = (int)uni((uint32_t)s1);
     }
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
-      const int acc = it & 1;
+      const uint32_t acc = it & 1;
       const uint32_t accph = (it >> 1) & 1;
       mbar_wait(&t_empty[acc], accph ^ 1, 300 + acc);
       tc_fence_after();
       if (lane == 0) TDX_TRACE(1, it);
-      const uint32_t d_tmem = tmem_base + acc * kAccCols;
-      // (Tried and dropped: probing the next chunk's barriers between the 24th and 25th MMA of a chunk, and splitting the
-      // epilogue warps into two groups that take alternate items -- both were slower end to end on B200.)
-      const bool steady = p.resident && it > 0;   // weights already in the ring: no per-stage handshakes
-      uint32_t accumulate = 0;
-      {
-        for (int s = s0; s < s1;) {
-          int seg, ch, tap0, taps;
-          stage_locate(p, s, seg, ch, tap0, taps);
-          const int tap1 = (taps - tap0 < s1 - s) ? taps : tap0 + (s1 - s);
-          mbar_wait(&a_full[sa], pha, 400 + sa);
-          tc_fence_after();
-          if (lane == 0 && s == s0) TDX_TRACE(2, it);
-          s += tap1 - tap0;
-          const uint32_t a16 = a_ring16 + sa * (kAStageBytes >> 4);
-          if (steady && taps == 9 && tap0 == 0 && tap1 == 9) {
-            // ---- 36 MMAs back to back
-            const uint32_t b16 = b_ring16 + sb * b_stage16;
+      const uint32_t d_tmem = uni(tmem_u + acc * kAccCols);
+      const bool steady = resident && it > 0;   // weights already in the ring: no per-stage handshakes
+      uint32_t accumulate = uni(0);
+      for (int s = s0; s < s1;) {
+        int seg, ch, tap0, taps;
+        stage_locate(p, s, seg, ch, tap0, taps);
+        // (the segment table is indexed dynamically, which ptxas cannot prove uniform: re-seed what the loop carries)
+        tap0 = (int)uni((uint32_t)tap0);
+        taps = (int)uni((uint32_t)taps);
+        const int tap1 = (taps - tap0 < s1 - s) ? taps : tap0 + (s1 - s);
+        mbar_wait(&a_full[sa], pha, 400 + sa);
+        tc_fence_after();
+        if (lane == 0 && s == s0) TDX_TRACE(2, it);
+        s += tap1 - tap0;
+        const uint32_t a_lo = a_lo0 + sa * (kAStageBytes >> 4);
+        if (steady && taps == 9 && tap0 == 0 && tap1 == 9) {
+          // ---- 36 MMAs back to back (resident ring: SB == stages_per_item, a chunk's 9 stages never wrap)
+          const uint32_t b_lo = b_lo0 + sb * b_stage16;
+          if (elect_one()) {
+            uint32_t bl = b_lo;
+#pragma unroll 1
+            for (int tap = 0; tap < 9; ++tap, bl += b_stage16) {
+              const uint32_t al = a_lo + (uint32_t)((0x16ad18b50820ull >> (5 * tap)) & 31ull);
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                umma_bf16(d_tmem, pack_desc(al + j * a_kstep16, a_h), pack_desc(bl + j * b_kstep16, b_h), idesc,
+                          (accumulate | tap | j) ? 1u : 0u);
+            }
+          }
+          __syncwarp();
+          accumulate = 1;
+          sb += 9;
+          if (sb >= SBu) { sb -= SBu; phb ^= 1; }
+        } else {
+          for (int tap = tap0; tap < tap1; ++tap) {
+            // tap offset (r * 10 + c pixels) from a packed table: 5 bits per tap; a 1x1 segment reads the patch centre
+            const uint32_t tapoff = taps == 9 ? (uint32_t)((0x16ad18b50820ull >> (5 * tap)) & 31ull) : (uint32_t)(kPatchW + 1);
+            const uint32_t b_lo = b_lo0 + sb * b_stage16;
+            if (!steady) {
+              mbar_wait(&b_full[sb], phb, 500 + sb);
+              tc_fence_after();
+            }
             if (elect_one()) {
 #pragma unroll
-              for (int tap = 0; tap < 9; ++tap) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const uint64_t adesc = a_hi | (uint64_t)(a16 + (tap / 3) * kPatchW + (tap % 3) + j * a_kstep16);
-                  const uint64_t bdesc = b_hi | (uint64_t)(b16 + tap * b_stage16 + j * b_kstep16);
-                  umma_bf16(d_tmem, adesc, bdesc, idesc, (accumulate | tap | j) ? 1u : 0u);
-                }
-              }
+              for (int j = 0; j < 4; ++j)
+                umma_bf16(d_tmem, pack_desc(a_lo + tapoff + j * a_kstep16, a_h), pack_desc(b_lo + j * b_kstep16, b_h),
+                          idesc, (accumulate | j) ? 1u : 0u);
+              if (!resident) umma_commit(&b_empty[sb]);
             }
             __syncwarp();
             accumulate = 1;
-            sb += 9;   // resident ring: SB == stages_per_item, a chunk's 9 stages never wrap
-            if (sb >= p.SB) { sb -= p.SB; phb ^= 1; }
-          } else {
-            for (int tap = tap0; tap < tap1; ++tap) {
-              const uint32_t tapoff = taps == 9 ? (uint32_t)((tap / 3) * kPatchW + (tap % 3)) : (uint32_t)(kPatchW + 1);
-              const uint32_t b16 = b_ring16 + sb * b_stage16;
-              if (!steady) {
-                mbar_wait(&b_full[sb], phb, 500 + sb);
-                tc_fence_after();
-              }
-              if (elect_one()) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const uint64_t adesc = a_hi | (uint64_t)(a16 + tapoff + j * a_kstep16);
-                  const uint64_t bdesc = b_hi | (uint64_t)(b16 + j * b_kstep16);
-                  umma_bf16(d_tmem, adesc, bdesc, idesc, (accumulate | j) ? 1u : 0u);
-                }
-                if (!p.resident) umma_commit(&b_empty[sb]);
-              }
-              __syncwarp();
-              accumulate = 1;
-              if (++sb == p.SB) { sb = 0; phb ^= 1; }
-            }
+            if (++sb == SBu) { sb = 0; phb ^= 1; }
           }
-          if (elect_one()) umma_commit(&a_empty[sa]);
-          __syncwarp();
-          if (++sa == kSA) { sa = 0; pha ^= 1; }
         }
+        if (elect_one()) umma_commit(&a_empty[sa]);
+        __syncwarp();
+        if (++sa == kSA) { sa = 0; pha ^= 1; }
       }
       if (elect_one()) umma_commit(&t_full[acc]);
       __syncwarp();
@@ -815,8 +833,8 @@ static int max_active_clusters(int csize) {
 
 // Choose the output-channel width of a work item (MMA N) and the split-K factor.  Model (cycles), from measurements
 // on B200:
-//   * an SS-mode M=128 K=16 tcgen05.mma costs max(86, N/2) cycles when issued stage by stage (~70 back to back from
-//     smem-resident weights) -- tools/probe/mma_probe.cu, tools/trace_igemm.py;
+//   * an SS-mode M=128 K=16 tcgen05.mma occupies the tensor pipe for max(48, N/2) cycles (tools/probe/mma_probe3.cu; the
+//     86 cycles of round 1 were R2UR-bound issue, not the pipe);
 //   * L2 -> SM delivers ~5 KB/clk chip-wide (tools/sweep_igemm.py) and ~56 B/clk into one SM; per item the A patches (23 KB per 64 input
 //     channels) and, unless the item's whole weight slice fits the B ring ("resident": loaded once per CTA), the
 //     weights (N*128 B per stage);
@@ -858,7 +876,7 @@ static ItemShape choose_item_shape(int cout, int tiles, int stages, int chunks, 
       grid -= grid % (nsplit * ks);
       if (grid <= 0) continue;
       const double rounds = (double)((items * ks + grid - 1) / grid);
-      const double cyc = n / 2.0 > 86.0 ? n / 2.0 : 86.0;
+      const double cyc = n / 2.0 > 48.0 ? n / 2.0 : 48.0;
       const double mma = rounds * my_stages * 4.0 * cyc + 800.0;
       const double a_bytes = (double)items * ks * my_chunks * kAStageBytes;
       const double b_bytes = resident ? (double)grid * stages * stage_bytes : (double)items * stages * stage_bytes;

@@ -39,9 +39,8 @@ class BlendCanvas:
         assert c == self.channels and tile.dtype == torch.float32 and tile.is_cuda
         tile = tile.contiguous()
         win = self.window(th) if window is None else window
-        L.check(L.lib().tdx_blend_accumulate(self.val.data_ptr(), self.wsum.data_ptr(), c, self.height, self.width,
-                                             tile.data_ptr(), win.data_ptr(), th, tw, y0 - self.origin[0],
-                                             x0 - self.origin[1], L.current_stream_ptr()))
+        L.call(L.lib().tdx_blend_accumulate, self.val.device, self.val.data_ptr(), self.wsum.data_ptr(), c, self.height,
+               self.width, tile.data_ptr(), win.data_ptr(), th, tw, y0 - self.origin[0], x0 - self.origin[1])
 
     def packed(self) -> torch.Tensor:
         """[C+1, H, W] un-normalised (sum x*w, sum w) -- what slicing a reference InfiniteTensor returns."""
@@ -49,6 +48,6 @@ class BlendCanvas:
 
     def normalized(self, divisor: float = 1.0) -> torch.Tensor:
         out = torch.empty_like(self.val)
-        L.check(L.lib().tdx_blend_normalize(out.data_ptr(), self.val.data_ptr(), self.wsum.data_ptr(), self.channels,
-                                            self.height * self.width, float(divisor), L.current_stream_ptr()))
+        L.call(L.lib().tdx_blend_normalize, self.val.device, out.data_ptr(), self.val.data_ptr(), self.wsum.data_ptr(),
+               self.channels, self.height * self.width, float(divisor))
         return out

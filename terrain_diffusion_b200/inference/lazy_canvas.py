@@ -62,8 +62,8 @@ class LazyCanvas:
         for by in range(y0 // b, (y0 + th - 1) // b + 1):
             for bx in range(x0 // b, (x0 + tw - 1) // b + 1):
                 blk = self._block(by, bx)
-                L.check(L.lib().tdx_canvas_add(blk.data_ptr(), c, b, b, tile.data_ptr(), th, tw, y0 - by * b,
-                                               x0 - bx * b, L.current_stream_ptr()))
+                L.call(L.lib().tdx_canvas_add, blk.device, blk.data_ptr(), c, b, b, tile.data_ptr(), th, tw, y0 - by * b,
+                       x0 - bx * b)
 
     def clear_cache(self):
         self.blocks.clear()

@@ -43,15 +43,16 @@ def gaussian_noise_patch(base_seed: int, y0: int, x0: int, h: int, w: int, chann
     if dev.type != "cuda":
         raise L.TdxError("gaussian_noise_patch (B200 path) generates on the GPU; there is no CPU path")
     nbytes = int(L.lib().tdx_noise_patch_workspace_bytes(channels, tile_h, tile_w))
-    key = (dev, nbytes)
+    # one scratch per (device, size, stream): two streams of one device must not share the counts / status words
+    key = (dev, nbytes, L.current_stream_ptr(dev))
     if key not in _workspaces:
         _workspaces[key] = torch.empty(nbytes, dtype=torch.uint8, device=dev)
     ws = _workspaces[key]
     out = torch.empty((channels, h, w), dtype=torch.float32, device=dev)
-    L.check(L.lib().tdx_noise_patch(int(base_seed) & MASK64, int(y0), int(x0), h, w, channels, tile_h, tile_w,
-                                    out.data_ptr(), ws.data_ptr(), nbytes, L.current_stream_ptr()))
+    L.call(L.lib().tdx_noise_patch, dev, int(base_seed) & MASK64, int(y0), int(x0), h, w, channels, tile_h, tile_w,
+           out.data_ptr(), ws.data_ptr(), nbytes)
     if check:
-        L.check(L.lib().tdx_noise_patch_status(ws.data_ptr(), L.current_stream_ptr()))
+        L.call(L.lib().tdx_noise_patch_status, dev, ws.data_ptr())
     return out
 
 
@@ -65,6 +66,5 @@ def standard_normal(seed: int, n: int, device="cuda") -> torch.Tensor:
         return out
     nbytes = int(L.lib().tdx_noise_patch_workspace_bytes(1, 1, n))
     ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-    L.check(L.lib().tdx_standard_normal(int(seed) & MASK64, n, out.data_ptr(), ws.data_ptr(), nbytes,
-                                        L.current_stream_ptr()))
+    L.call(L.lib().tdx_standard_normal, dev, int(seed) & MASK64, n, out.data_ptr(), ws.data_ptr(), nbytes)
     return out

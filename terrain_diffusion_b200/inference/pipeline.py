@@ -17,6 +17,11 @@ from .lazy_canvas import LazyCanvas, TensorWindow
 from .stages import coarse_stage_tile, decoder_stage_tile, latent_stage_tiles
 from .tiling import linear_weight_window
 
+# seed offsets of the latent stage's noise fields: _build_latent_stage (world_pipeline.py:1133-1203) passes 5819 to the
+# init phase and 5820 + i to the i-th T_INTER phase (pinned against the reference source by tests/golden/stages_golden.npz)
+LATENT_INIT_SEED_OFFSET = 5819
+LATENT_STEP_SEED_OFFSET = 5820
+
 
 class TerrainPipeline:
     def __init__(self, coarse_model, base_model, decoder_model, seed: int, conditioning_fn, *, coarse_means, coarse_stds,
@@ -60,14 +65,15 @@ class TerrainPipeline:
 
         def f_lat1(ctxs, coarse_windows):
             return latent_stage_tiles(self.base_model, self.seed, ctxs, None, coarse_windows, self.t_init, ww64,
-                                      self.histogram_raw, self.lat_means, self.lat_stds, seed_offset=5820)
+                                      self.histogram_raw, self.lat_means, self.lat_stds, seed_offset=LATENT_INIT_SEED_OFFSET)
 
         self.latents_init = LazyCanvas(6, f_lat1, out_w, dev, args=(self.coarse,), args_windows=(coarse_w,),
                                        batch_size=latents_batch_size)
 
         def f_lat2(ctxs, prev_windows, coarse_windows):
             return latent_stage_tiles(self.base_model, self.seed, ctxs, prev_windows, coarse_windows, self.t_inter,
-                                      ww64, self.histogram_raw, self.lat_means, self.lat_stds, seed_offset=5821)
+                                      ww64, self.histogram_raw, self.lat_means, self.lat_stds,
+                                      seed_offset=LATENT_STEP_SEED_OFFSET)
 
         self.latents = LazyCanvas(6, f_lat2, out_w, dev, args=(self.latents_init, self.coarse),
                                   args_windows=(out_w, coarse_w), batch_size=latents_batch_size)

@@ -11,11 +11,27 @@ from __future__ import annotations
 
 import ctypes as C
 
+import functools
+
 import torch
 
 from .. import _lib as L
 
 LOWFREQ_MEAN, LOWFREQ_STD = -31.4, 38.6          # world_pipeline.py:1280-1281
+
+
+def _on_arg_device(fn):
+    """Run `fn` with the CUDA device of its first device-carrying argument (tensor or canvas) current: libtdx launches
+    on the current device and on its current stream (L.current_stream_ptr())."""
+    @functools.wraps(fn)
+    def wrapper(*a, **k):
+        for v in list(a) + list(k.values()):
+            dev = getattr(v, "device", None)
+            if isinstance(dev, torch.device) and dev.type == "cuda":
+                with torch.cuda.device(dev):
+                    return fn(*a, **k)
+        return fn(*a, **k)
+    return wrapper
 
 
 def _chk(x: torch.Tensor, name: str) -> torch.Tensor:
@@ -39,6 +55,7 @@ def _resized_output_size(h: int, w: int, size) -> tuple[int, int]:
     return new_h, new_w
 
 
+@_on_arg_device
 def resize_bilinear(x: torch.Tensor, size) -> torch.Tensor:
     """TF.resize(x, size, interpolation=BILINEAR) for an fp32 tensor (antialias on): width pass, then height pass."""
     x = _chk(x, "resize_bilinear")
@@ -56,6 +73,7 @@ def resize_bilinear(x: torch.Tensor, size) -> torch.Tensor:
     return x
 
 
+@_on_arg_device
 def pad_linear_extrapolation(x: torch.Tensor) -> torch.Tensor:
     x = _chk(x, "pad_linear_extrapolation")
     h, w = x.shape
@@ -74,6 +92,7 @@ def resize_extrapolated(x: torch.Tensor, size) -> torch.Tensor:
     return out[ph:ph + th, pw:pw + tw]
 
 
+@_on_arg_device
 def gaussian_blur(x: torch.Tensor, kernel_size: int, sigma: float) -> torch.Tensor:
     x = _chk(x, "gaussian_blur")
     h, w = x.shape
@@ -82,6 +101,7 @@ def gaussian_blur(x: torch.Tensor, kernel_size: int, sigma: float) -> torch.Tens
     return out
 
 
+@_on_arg_device
 def _combine(a: torch.Tensor, b: torch.Tensor, signed_square: bool = False, int16: bool = False):
     """f(a + b) over two equally shaped (possibly strided-row) views."""
     assert a.shape == b.shape and a.stride(1) == 1 and b.stride(1) == 1
@@ -122,6 +142,7 @@ def padded_window(i1: int, j1: int, i2: int, j2: int, scale: int, sigma: float =
     return pi1, pj1, pi2, pj2
 
 
+@_on_arg_device
 def compute_elev(residual_canvas, latents_canvas, i1: int, j1: int, i2: int, j2: int, scale: int, residual_mean: float,
                  residual_std: float, sigma: float = 5, as_int16: bool = False):
     """Elevation in metres over pixel rows [i1, i2) x columns [j1, j2) (world_pipeline.py:1277-1313).
@@ -153,6 +174,7 @@ def compute_elev(residual_canvas, latents_canvas, i1: int, j1: int, i2: int, j2:
     return _combine(residual_p[oi:oi + h, oj:oj + w], up[oi:oi + h, oj:oj + w], signed_square=True, int16=as_int16)
 
 
+@_on_arg_device
 def compute_climate(coarse_canvas, i1: int, j1: int, i2: int, j2: int, elev: torch.Tensor, scale: int) -> torch.Tensor:
     """Climate over pixel rows [i1, i2) x columns [j1, j2) (WorldPipeline._compute_climate, world_pipeline.py:1314-1365):
     fp32 CUDA [5, H, W] = {temperature with the local lapse-rate correction, coarse channels 3, 4, 5, lapse rate}.

@@ -29,9 +29,15 @@ def _solve_cache(model):
 
 
 def get_diffusion_solve(model, scheduler, n, h, w, num_steps) -> DiffusionSolve:
+    """Cached fused N-step solve.  The key is everything the solve bakes in: the sigma table and the per-step order
+    schedule (they cover sigma_min/max/rho/schedule, scaling_p/scaling_t, lower_order_final, euler_at_final, ...) plus
+    the options that change the update formula.  The caller's scheduler is put in the state the reference leaves it in
+    (`set_timesteps(num_steps)`) on a cache hit too."""
+    scheduler.set_timesteps(num_steps)
     c = scheduler.config
-    key = (n, h, w, num_steps, c.sigma_min, c.sigma_max, c.sigma_data, c.rho, c.sigma_schedule, c.prediction_type,
-           c.final_sigmas_type, c.solver_order, id(model.folded()))
+    key = (n, h, w, num_steps, tuple(float(v) for v in scheduler.sigmas), tuple(scheduler.order_schedule()),
+           float(c.sigma_data), c.prediction_type, c.final_sigmas_type, c.solver_order, c.algorithm_type, c.solver_type,
+           id(model.folded()))
     cache = _solve_cache(model)
     if key not in cache:
         cache[key] = DiffusionSolve(model, scheduler, n, h, w, num_steps)

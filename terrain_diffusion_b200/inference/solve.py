@@ -33,7 +33,7 @@ class DiffusionSolve:
         self.sample = torch.zeros((n, cs, h, w), dtype=torch.float32, device=dev)
         self.cond = torch.zeros((n, max(cc, 1), h, w), dtype=torch.float32, device=dev)
         self.x0_prev = torch.zeros_like(self.sample)
-        self.prog = UNetProgram()
+        self.prog = UNetProgram(fw.device)
         # the noise labels of all steps are known up front: ONE embed launch produces every step's modulation vectors
         em = UNetEmitter(fw, n, h, w, cvec_sets=num_steps)
         self.host_emb = len(model.conditional_layers) > 0 or not fw.pos_emb

@@ -242,7 +242,7 @@ class EDMUnet2D(nn.Module):
                 labels=torch.zeros((n,), dtype=torch.float32, device=dev),
                 emb=torch.zeros((n, fw.emb_channels), dtype=torch.float32, device=dev) if with_emb else None,
                 out=torch.zeros((n, fw.out_channels, h, w), dtype=torch.float32, device=dev))
-            prog = UNetProgram()
+            prog = UNetProgram(dev)
             em.emit_embed(prog, labels=bufs.labels, emb_in=bufs.emb)
             em.emit(prog, [(bufs.x, fw.in_channels, None)], model_out=bufs.out)
             self._plans[key] = (prog, bufs)

@@ -91,11 +91,16 @@ def block_plan(cfg: dict) -> tuple[list, list]:
 
 
 class FoldedWeights:
-    """Device-resident effective weights of one model (fp32 small tensors + packed bf16 GEMM operands)."""
+    """Device-resident effective weights of one model (fp32 small tensors + packed bf16 GEMM operands).
+
+    The fold itself (normalise, gains, mp_sum / mp_concat constants, bf16 rounding, B-stage packing) is host arithmetic
+    on the fp32 master weights, done once: the results are uploaded with plain copies, so creating a model puts no
+    kernel on the device (the reference re-normalises 130 tensors with ~7 launches each on EVERY forward)."""
 
     def __init__(self, model, device):
         cfg = dict(model.config)
-        sd = {k: v.detach().to(device=device, dtype=torch.float32) for k, v in model.state_dict().items()}
+        sd = {k: v.detach().cpu().to(torch.float32) for k, v in model.state_dict().items()}
+        dev_arg, device = device, torch.device("cpu")      # fold on the host; upload at the end of __init__
         self.cfg = cfg
         self.device = device
         enc, dec = block_plan(cfg)
@@ -201,19 +206,24 @@ class FoldedWeights:
                         assert ws is None, "decoder block without concat but with a skip conv is not planned"
                         seg[p + "res0"] = [w0.bfloat16()]
                         seg[p + "res1"] = [w1.bfloat16()]
+        self.device = dev_arg
+        for k in list(g):
+            g[k] = g[k].to(dev_arg)
 
     def packed(self, key: str, n_per_item: int) -> torch.Tensor:
         """bf16 B operand of GEMM `key` packed for work items of `n_per_item` output channels (cached)."""
         ck = (key, n_per_item)
         if ck not in self._packed:
-            self._packed[ck] = pack_weight_segments([w.float() for w in self.segs[key]], n_per_item)
+            self._packed[ck] = pack_weight_segments([w.float() for w in self.segs[key]], n_per_item).to(self.device)
         return self._packed[ck]
 
 
 class UNetProgram:
     """One compiled launch list (single forward, or a whole N-step solve) + the buffers it owns."""
 
-    def __init__(self):
+    def __init__(self, device=None):
+        import torch as _t
+        self.device = _t.device("cuda", _t.cuda.current_device()) if device is None else _t.device(device)
         self.handle = C.c_void_p()
         L.check(L.lib().tdx_program_create(C.byref(self.handle)))
         self.keep: list = []
@@ -222,17 +232,17 @@ class UNetProgram:
         self.n_launch = 0
 
     def run(self, use_graph: bool = True):
-        L.check(L.lib().tdx_program_run(self.handle, 1 if use_graph else 0, L.current_stream_ptr()))
+        L.call(L.lib().tdx_program_run, self.device, self.handle, 1 if use_graph else 0)
 
     def instantiate(self):
-        L.check(L.lib().tdx_program_instantiate(self.handle, L.current_stream_ptr()))
+        L.call(L.lib().tdx_program_instantiate, self.device, self.handle)
 
     def profile(self):
         """Eager run with per-launch CUDA events: returns (ms list, kind list) in program order."""
         n = L.lib().tdx_program_num_launches(self.handle)
         ms = (C.c_float * n)()
         kinds = (C.c_int32 * n)()
-        L.check(L.lib().tdx_program_profile(self.handle, ms, kinds, L.current_stream_ptr()))
+        L.call(L.lib().tdx_program_profile, self.device, self.handle, ms, kinds)
         return list(ms), list(kinds)
 
     def __del__(self):

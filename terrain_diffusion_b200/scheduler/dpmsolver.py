@@ -217,8 +217,8 @@ class EDMDPMSolverMultistepScheduler:
         f = model_output.detach().to(torch.float32).contiguous()
         if self._x0_prev is None or self._x0_prev.shape != x.shape or self._x0_prev.device != x.device:
             self._x0_prev = torch.zeros_like(x)
-        L.check(L.lib().tdx_sched_step(x.data_ptr(), f.data_ptr(), self._x0_prev.data_ptr(), x.numel(), co["c_skip"],
-                                       co["c_out"], co["r"], co["k"], L.current_stream_ptr()))
+        L.call(L.lib().tdx_sched_step, x.device, x.data_ptr(), f.data_ptr(), self._x0_prev.data_ptr(), x.numel(),
+               co["c_skip"], co["c_out"], co["r"], co["k"])
         if self.lower_order_nums < c.solver_order:
             self.lower_order_nums += 1
         self._step_index += 1

@@ -24,6 +24,9 @@ def stage_inputs():
     d["coarse_means"] = torch.randn(6, generator=g) * 0.2
     d["coarse_stds"] = torch.rand(6, generator=g) + 0.5
     d["cond_snr"] = torch.tensor([0.3, 0.5, 1.0, 2.0, 4.0])
+    # appended last so the tensors above keep their values: the product decoder window (512 / 8 = 64 latent pixels)
+    d["dec_latents_512"] = torch.cat([torch.randn(5, 64, 64, generator=g) * 0.6, torch.rand(1, 64, 64, generator=g) + 0.5])
+    d["dec_latents_512"][:5] *= d["dec_latents_512"][5:]
     return d
 
 

@@ -53,6 +53,24 @@ def extract():
     return ns
 
 
+def latent_seed_offsets():
+    """The seed_offset constants of the reference's _build_latent_stage call sites (world_pipeline.py:1133-1203):
+    [init phase, first T_INTER phase] -- read from the source so the pipeline's wiring is pinned, not assumed."""
+    src = (REF / "terrain_diffusion/inference/world_pipeline.py").read_text()
+    vals = set()
+    for n in ast.walk(ast.parse(src)):
+        if isinstance(n, ast.FunctionDef) and n.name == "_build_latent_stage":
+            for kw in (k for c in ast.walk(n) if isinstance(c, ast.Call) for k in c.keywords):
+                if kw.arg != "seed_offset":
+                    continue
+                v = kw.value
+                if isinstance(v, ast.Constant):
+                    vals.add(int(v.value))
+                elif isinstance(v, ast.BinOp) and isinstance(v.left, ast.Constant):   # 5820 + i
+                    vals.add(int(v.left.value))
+    return sorted(vals)
+
+
 def build(cfg):
     m = EDMUnet2D(**cfg).eval()
     m.load_state_dict(O.procedural_state_dict(cfg, seed=0))
@@ -62,6 +80,9 @@ def build(cfg):
 def main():
     ns = extract()
     out = {}
+    offs = latent_seed_offsets()
+    assert len(offs) == 2, offs
+    out["latent_seed_offsets"] = np.asarray(offs, dtype=np.int64)
     inp = stage_inputs()
     sched = EDMDPMSolverMultistepScheduler(sigma_min=0.002, sigma_max=80, sigma_data=0.5)
 
@@ -75,6 +96,10 @@ def main():
                                                     96).numpy()
     out["decoder_2step"] = ns["_decoder_inference"](fake, (0, 2, -1), inp["dec_latents"].clone(), sched, ww,
                                                     [t0, torch.arctan(torch.tensor(0.065) / 0.5)], 128, 96).numpy()
+    # the product geometry (tile 512 / stride 384, world_pipeline.py:313-314), stored 4x sub-sampled to stay small
+    ww512 = ns["linear_weight_window"](512, "cpu", torch.float32)
+    full = ns["_decoder_inference"](fake, (0, -1, 3), inp["dec_latents_512"].clone(), sched, ww512, [t0], 512, 384)
+    out["decoder_512_sub4"] = full[:, ::4, ::4].contiguous().numpy()
     del dec
 
     # ---------------- latent stage: batch of two windows, phase 1 (samples=None) then phase 2 on phase-1 output
@@ -88,11 +113,11 @@ def main():
     t_inter = float(torch.atan(torch.tensor(0.35) / 0.5))
     conds = [c.clone() for c in inp["lat_cond"]]
     p1 = ns["_latent_inference"](fake, ctxs, None, conds, t_init, sched, ww64, inp["lat_hist"], inp["lat_means"],
-                                 inp["lat_stds"], seed_offset=5820)
+                                 inp["lat_stds"], seed_offset=offs[0])
     out["latent_phase1"] = torch.stack(p1).numpy()
     conds = [c.clone() for c in inp["lat_cond"]]
     p2 = ns["_latent_inference"](fake, ctxs, [p.clone() for p in p1], conds, t_inter, sched, ww64, inp["lat_hist"],
-                                 inp["lat_means"], inp["lat_stds"], seed_offset=5821)
+                                 inp["lat_means"], inp["lat_stds"], seed_offset=offs[1])
     out["latent_phase2"] = torch.stack(p2).numpy()
     out["latent_condvec"] = ns["_process_latent_conditioning"](
         fake, torch.cat([inp["lat_cond"][0][:-1] / inp["lat_cond"][0][-1:], torch.ones(1, 4, 4)])[None],

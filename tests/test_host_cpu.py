@@ -177,3 +177,15 @@ def test_new_entry_points_validate_their_arguments_without_a_gpu():
     assert b"window" in lib.tdx_last_error()
     assert lib.tdx_climate_sample(p, p, p, 4, 20, 20, 7, p, 0, 0, 8, 8, 256, 0, 0, q, None) != 0
     assert b"channels" in lib.tdx_last_error()
+
+
+def test_latent_stage_seed_offsets_match_the_reference_call_sites():
+    """_build_latent_stage passes seed_offset 5819 to the init phase and 5820 + i to phase i
+    (world_pipeline.py:1133-1203).  tests/golden/make_golden_stages.py reads both out of the reference SOURCE with ast
+    and stores them; the pipeline's wiring constants must be those, or the same world seed gives different latents."""
+    from pathlib import Path
+    from terrain_diffusion_b200.inference import pipeline
+    g = np.load(Path(__file__).resolve().parent / "golden" / "stages_golden.npz")
+    offs = [int(v) for v in g["latent_seed_offsets"]]
+    assert offs == [5819, 5820]
+    assert [pipeline.LATENT_INIT_SEED_OFFSET, pipeline.LATENT_STEP_SEED_OFFSET] == offs

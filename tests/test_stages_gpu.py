@@ -63,13 +63,14 @@ def test_latent_conditioning_vector_and_stage_match_reference_method():
     sig0 = float(EDMDPMSolverMultistepScheduler().sigmas[0])
     ctxs = [(0, 1, 2), (0, -1, 0)]
     p1 = latent_stage_tiles(m, SEED, ctxs, None, [c.clone() for c in inp["lat_cond"]], math.atan(sig0 / 0.5), ww,
-                            inp["lat_hist"], inp["lat_means"], inp["lat_stds"], seed_offset=5820, pad_batch_to=16)
+                            inp["lat_hist"], inp["lat_means"], inp["lat_stds"], seed_offset=int(G["latent_seed_offsets"][0]),
+                            pad_batch_to=16)
     for got, want in zip(p1, G["latent_phase1"]):
         check_packed(got, want)
     # phase 2 consumes the REFERENCE's phase-1 tiles so the two phases are checked independently
     prev = [torch.from_numpy(x) for x in G["latent_phase1"]]
     p2 = latent_stage_tiles(m, SEED, ctxs, prev, [c.clone() for c in inp["lat_cond"]], math.atan(0.35 / 0.5), ww,
-                            inp["lat_hist"], inp["lat_means"], inp["lat_stds"], seed_offset=5821)
+                            inp["lat_hist"], inp["lat_means"], inp["lat_stds"], seed_offset=int(G["latent_seed_offsets"][1]))
     for got, want in zip(p2, G["latent_phase2"]):
         check_packed(got, want)
 
