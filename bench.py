@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- denoising steps/sec on 256x256 tiles of the 30m decoder U-Net (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--tiles B] [--size S]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference|reference-gpu] [--tiles B] [--size S]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W
 
@@ -192,16 +192,178 @@ def run_reference_arm(args, rank):
     print(json.dumps(line), flush=True)
 
 
+# ----------------------------------------------------------------------------------------------------- GPU reference
+def run_reference_gpu_arm(args, rank):
+    """The stated "kernel to beat" (BASELINE.md section 4): the reference algorithm itself on the same B200
+    through PyTorch library kernels -- bf16 eager (cuDNN / cuBLAS / ATen elementwise, weight re-normalisation every
+    forward, like WorldPipeline with dtype='bf16') and under torch.compile (Inductor, world_pipeline.py:421-430).  The
+    reference tree cannot travel to the GPU box, so the model is its oracle restatement (bit-compatible in fp32 with the
+    reference, tests/test_oracle_golden.py) moved to the device; comparison arm only, never the default."""
+    if rank != 0:
+        return
+    from oracle import scheduler as osched
+    from oracle import unet as ounet
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    cfg = ounet.DECODER_CFG
+    B, S = args.tiles, args.size
+    sd = {k: v.to(dev) for k, v in ounet.procedural_state_dict(cfg, seed=0).items()}
+    g = torch.Generator().manual_seed(1)
+    noise = (torch.randn(B, 1, S, S, generator=g) * 80).to(dev)
+    cond = torch.randn(B, 4, S, S, generator=g).to(dev).bfloat16()
+
+    def fwd(x, t):
+        return ounet.unet_forward(sd, cfg, x, t, [])
+
+    results = {}
+    variants = [("eager_bf16", fwd)]
+    try:
+        variants.append(("compile_bf16", torch.compile(fwd)))
+    except Exception as e:  # pragma: no cover
+        results["compile_bf16"] = {"unavailable": repr(e)[:200]}
+    for name, f in variants:
+        try:
+            def solve(n_steps):
+                sch = osched.OracleScheduler()
+                sch.set_timesteps(SOLVE_STEPS)
+                sch.sigmas, sch.timesteps = sch.sigmas.to(dev), sch.timesteps.to(dev)
+                x = noise.clone()
+                for i, (t, sigma) in enumerate(zip(sch.timesteps, sch.sigmas)):
+                    if i >= n_steps:
+                        break
+                    scaled = sch.precondition_inputs(x, sigma).bfloat16()
+                    lab = sch.trigflow_precondition_noise(sigma.view(-1)).expand(B).bfloat16()
+                    mo = f(torch.cat([scaled, cond], dim=1), lab).float()
+                    sch.step_index = i                      # no .item() sync inside the timed loop
+                    x = sch.step(mo, t, x)
+                return x
+            with torch.no_grad():
+                solve(max(args.warmup, 3))
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                done = 0
+                e0.record()
+                while done < args.steps:
+                    n = min(SOLVE_STEPS, args.steps - done)
+                    solve(n)
+                    done += n
+                e1.record()
+                torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+            results[name] = {"value": B * args.steps / (ms / 1e3), "unit": UNIT, "ms_per_step": ms / args.steps}
+        except Exception as e:  # pragma: no cover
+            results[name] = {"unavailable": repr(e)[:300]}
+    best = max((r["value"] for r in results.values() if "value" in r), default=None)
+    line = {"impl": "reference-gpu", "metric": METRIC, "value": best, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": (1e3 * B / best) if best else None, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"configs[1]: 30m decoder U-Net, {B} x {S}x{S} tile, 20-step DPM-Solver++ -- the "
+                                   "reference algorithm (oracle restatement) through PyTorch library kernels on the GPU",
+                       "tiles_per_gpu": B, "tile": S, "solve_steps": SOLVE_STEPS},
+            "variants": results, "gpu_launches": 0,
+            "note": "comparison arm (the stated kernel to beat), PyTorch/cuDNN/Inductor kernels; not the product"}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------- canvas arm
+CANVASES = {
+    # BASELINE configs[2]: 4 x 4 = 16 overlapping 512-px tiles at stride 384 (training/evaluation/__init__.py:16-22 gives
+    # starts [0, 384, 768, 1152] for 1664 px; "2048 px" in BASELINE.json is not reachable with the reference's strides)
+    "canvas": dict(size=1664, tile=512, stride=384, name="configs[2]: 1664^2 canvas, 4x4 tiles of 512 @ stride 384"),
+    # configs[3]-shaped export canvas: 24 x 24 = 576 tiles (9344^2 px); 8192^2 itself gives 21 (bounded) or 23 (window
+    # indexing) tile rows, neither of which stripes evenly over 8 GPUs
+    "export": dict(size=9344, tile=512, stride=384, name="configs[3]-shaped: 9344^2 canvas, 24x24 tiles of 512 @ stride 384"),
+}
+
+
+def run_canvas_arm(args, rank, local_rank, world):
+    """Strong scaling of ONE canvas: tile rows striped over the ranks, overlap strips exchanged with the neighbours
+    while the interior tiles are solved (inference/sharded.py), result bit-identical to the single-GPU canvas."""
+    import torch.distributed as dist
+    from terrain_diffusion_b200.inference import sample_decoder_diffusion_sharded
+    from terrain_diffusion_b200.inference.sharded import ShardedCanvas
+    from terrain_diffusion_b200.models import EDMUnet2D
+    from terrain_diffusion_b200.scheduler import EDMDPMSolverMultistepScheduler
+    from oracle import unet as ounet
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29533")
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    else:
+        dist.init_process_group("gloo", rank=0, world_size=1)      # ShardedCanvas speaks torch.distributed
+    cv = CANVASES[args.workload]
+    H, T, S_ = cv["size"], cv["tile"], cv["stride"]
+    cfg = ounet.DECODER_CFG
+    model = EDMUnet2D(**cfg).eval()
+    model.load_state_dict(ounet.procedural_state_dict(cfg, seed=0))
+    model = model.to(dev)
+    sched = EDMDPMSolverMultistepScheduler()
+    g = torch.Generator().manual_seed(5)                            # every rank holds the same input canvas
+    noise = (torch.randn(1, 1, H, H, generator=g) * 80).to(dev)
+    cond = torch.randn(1, 4, H, H, generator=g).to(dev)
+    steps = args.solve_steps
+    probe = ShardedCanvas(1, H, H, T, S_, dev)
+    n_tiles = len(probe.row_starts) * len(probe.col_starts)
+    halo = (probe._strip_rows() + probe._upper_rows()) * H * 2 * 4
+    del probe
+
+    def solve():
+        return sample_decoder_diffusion_sharded(model, sched, cond, noise, T, S_, num_steps=steps,
+                                                tile_batch=args.tile_batch)
+    solve()                                                         # warm-up: plans, graphs, NCCL connections
+    torch.cuda.synchronize()
+    reps = max(1, -(-args.steps // steps))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    with ClockSampler(local_rank) as clk:
+        e0.record()
+        for _ in range(reps):
+            own, (lo, hi) = solve()
+        e1.record()
+        torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t_ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms = float(t_ms.item())
+    value = n_tiles * steps * reps / (ms / 1e3)
+    if rank == 0:
+        line = {"metric": METRIC.replace("256^2", f"{T}^2"), "value": value, "unit": UNIT, "n_gpus": world,
+                "steps": reps * steps, "warmup": steps, "ms_per_step": ms / (reps * steps), "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": f"{cv['name']}, {steps}-step solves per tile, blended; rows striped over "
+                                       f"{world} GPU(s) with neighbour strip exchange", "canvas": H, "tile": T,
+                           "stride": S_, "tiles": n_tiles, "solve_steps": steps, "tile_batch": args.tile_batch,
+                           "halo_bytes_per_rank_per_solve": halo, "parallelism": f"tile-row stripes x{world}",
+                           "l2": "every tile solve streams > 1 GB of activations (> 126 MB L2)"},
+                "clocks": clk.summary(), "tflops": value * GFLOP_PER_STEP_256 * (T / 256.0) ** 2 / 1e3,
+                "owned_rows": [lo, hi]}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+    dist.destroy_process_group()
+
+
 # ----------------------------------------------------------------------------------------------------- our arm
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-gpu"])
     ap.add_argument("--tiles", type=int, default=1, help="independent tiles solved together per GPU")
     ap.add_argument("--size", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="tiles", choices=["tiles", "canvas", "export"],
+                    help="tiles (default, the BASELINE metric: independent 256^2 tiles per GPU, weak scaling) | canvas "
+                         "(configs[2]: one 1664^2 canvas, strong scaling) | export (configs[3]-shaped 9344^2 canvas)")
+    ap.add_argument("--solve-steps", type=int, default=SOLVE_STEPS, help="denoising steps per tile (canvas workloads)")
+    ap.add_argument("--tile-batch", type=int, default=4, help="tiles solved together per launch (canvas workloads)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -212,6 +374,12 @@ def main():
 
     if args.impl == "reference":
         run_reference_arm(args, rank)
+        return
+    if args.impl == "reference-gpu":
+        run_reference_gpu_arm(args, rank)
+        return
+    if args.workload != "tiles":
+        run_canvas_arm(args, rank, local_rank, world)
         return
 
     import torch.distributed as dist

@@ -73,6 +73,18 @@ typedef struct TdxIgemmDesc {
   float resid_scale;
   float clip;              /* > 0: v = clamp(v, -clip, +clip) after the residual (unet_block.py:153-154); 0: off  */
   TdxOutSpec out[3];
+  /* Pixel-norm side channel (fp32 [n_img][H][W] planes).  A launch that computes the pixel-norm of its result (a
+   * TDX_OUT_PNORM_SILU output or TDX_EPI_PNORM) can also store the per-pixel factor 1 / (1e-4 + rms over c_out) in
+   * rms_out; the launch that later adds pixelnorm(that tensor) as its residual passes the plane as resid_inv (with
+   * resid_pnorm = 0: r' = r * resid_inv[pixel], at the residual's resolution) instead of re-reading every channel of
+   * the residual to recompute it.  Both may be NULL. */
+  float* rms_out;
+  const float* resid_inv;
+  /* Split-K factor: 0 = the library's cost model picks it (together with the residency of the weights); > 0 forces it
+   * (the launch fails with TDX_E_INVALID when that split is impossible for the shape).  Used with n_per_item by the
+   * measured per-shape table terrain_diffusion_b200/tuned_shapes.json (tools/tune_igemm.py). */
+  int32_t k_split;
+  int32_t _reserved;
 } TdxIgemmDesc;
 
 /* Output channels per work item (64/128/192/256) the library prefers for this launch shape: balances the MMA issue

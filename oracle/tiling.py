@@ -111,3 +111,57 @@ def sample_decoder_consistency_tiled(model_fn, sigma_data, sigma0, cond_img, noi
                 samples = torch.cos(t) * x_t - torch.sin(t) * sigma_data * pred
             accumulate(out, out_w, samples, weights, i0, j0)
     return normalise(out, out_w) / sigma_data
+
+
+# ---------------------------------------------------------------------------------------------- multi-phase
+def build_timestep_ranges(all_timesteps: torch.Tensor, thresholds) -> list:
+    """annotated_infinite_panorama.py:84-102: descending timesteps split at the (descending-sorted) thresholds."""
+    thresholds = sorted(thresholds, reverse=True)
+    if not thresholds:
+        return [all_timesteps]
+    ranges, prev = [], None
+    for t in thresholds:
+        r = all_timesteps[all_timesteps >= t] if prev is None else \
+            all_timesteps[(all_timesteps >= t) & (all_timesteps < prev)]
+        if len(r) > 0:
+            ranges.append(r)
+        prev = t
+    tail = all_timesteps[all_timesteps < thresholds[-1]]
+    if len(tail) > 0:
+        ranges.append(tail)
+    return ranges
+
+
+@torch.no_grad()
+def sample_infinite_diffusion(model_fn, make_scheduler, cond_img, noise, tile_size, tile_stride, num_steps, thresholds):
+    """Dense multi-phase InfiniteDiffusion on a bounded canvas, fp32: the phase structure of
+    annotated_infinite_panorama.py:176-226 (initial phase from the noise field, continuation phases from the BLENDED
+    previous phase) in the loop shape of evaluation/infinite_consistency.py:207-239 (per phase: all tiles row-major ->
+    weighted sum -> divide), with the diffusion step of sample_diffusion_decoder.py:105-120 inside and a per-tile
+    scheduler reset at every phase start (no multistep history survives the blend).  noise is already scaled by
+    sigma_0."""
+    b, c, h, w = noise.shape
+    weights = linear_weight_window(tile_size, noise.dtype)[None, None]
+    probe = make_scheduler()
+    probe.set_timesteps(num_steps)
+    sample = noise
+    i0s = 0
+    for rng in build_timestep_ranges(probe.timesteps, thresholds):
+        out = torch.zeros_like(noise)
+        out_w = torch.zeros_like(noise)
+        for i0 in tile_starts(h, tile_size, tile_stride):
+            for j0 in tile_starts(w, tile_size, tile_stride):
+                sch = make_scheduler()
+                sch.set_timesteps(num_steps)
+                sch.step_index = i0s                      # positioned at the phase's first step, empty history
+                x = sample[..., i0:i0 + tile_size, j0:j0 + tile_size]
+                tc = cond_img[..., i0:i0 + tile_size, j0:j0 + tile_size]
+                for k in range(i0s, i0s + len(rng)):
+                    sigma = sch.sigmas[k]
+                    scaled = sch.precondition_inputs(x, sigma)
+                    cnoise = sch.trigflow_precondition_noise(sigma.view(-1).expand(b))
+                    x = sch.step(model_fn(torch.cat([scaled, tc], dim=1), cnoise), sch.timesteps[k], x)
+                accumulate(out, out_w, x, weights, i0, j0)
+        sample = normalise(out, out_w)
+        i0s += len(rng)
+    return sample

@@ -49,11 +49,11 @@ def mp_silu(x):
 def mp_sum(args, w):
     """mp_layers.py:47-62; weights are materialised in the activation dtype (fp32 here)."""
     if w is None:
-        wt = torch.full((len(args),), 1 / len(args), dtype=args[0].dtype)
+        wt = torch.full((len(args),), 1 / len(args), dtype=args[0].dtype, device=args[0].device)
     elif isinstance(w, float):
-        wt = torch.tensor([1 - w, w], dtype=args[0].dtype)
+        wt = torch.tensor([1 - w, w], dtype=args[0].dtype, device=args[0].device)
     else:
-        wt = torch.tensor(w, dtype=args[0].dtype)
+        wt = torch.tensor(w, dtype=args[0].dtype, device=args[0].device)
     acc = sum(a * wi for a, wi in zip(args, wt))
     return acc / torch.linalg.vector_norm(wt)
 
@@ -61,10 +61,10 @@ def mp_sum(args, w):
 def mp_concat(args, w, dim=1):
     """mp_layers.py:65-86."""
     if isinstance(w, float):
-        wt = torch.tensor([1 - w, w], dtype=args[0].dtype)
+        wt = torch.tensor([1 - w, w], dtype=args[0].dtype, device=args[0].device)
     else:
-        wt = torch.tensor(w, dtype=args[0].dtype)
-    n_tot = torch.tensor(sum(a.shape[dim] for a in args), dtype=args[0].dtype)
+        wt = torch.tensor(w, dtype=args[0].dtype, device=args[0].device)
+    n_tot = torch.tensor(sum(a.shape[dim] for a in args), dtype=args[0].dtype, device=args[0].device)
     c = torch.sqrt(n_tot / torch.sum(torch.square(wt)))
     return torch.cat([a * (c / np.sqrt(a.shape[dim]) * wt[i]) for i, a in enumerate(args)], dim=dim)
 
@@ -78,7 +78,7 @@ def mp_concat_scales(n_a: int, n_b: int, t: float) -> tuple[float, float]:
 def positional_embedding(t: torch.Tensor, num_channels: int) -> torch.Tensor:
     """MPPositionalEmbedding, mp_layers.py:88-107."""
     half = num_channels // 2
-    freqs = torch.exp(torch.arange(half) * -(math.log(10) / (half - 1)))
+    freqs = torch.exp(torch.arange(half, device=t.device) * -(math.log(10) / (half - 1)))
     y = t.to(torch.float32).outer(freqs.to(torch.float32))
     return (torch.cat([torch.sin(y), torch.cos(y)], dim=1) * np.sqrt(2)).to(t.dtype)
 
@@ -155,7 +155,7 @@ def _attn(x, sd, prefix, num_heads):
     y = mp_conv(x, sd[prefix + "attn_qkv.weight"])
     y = y.reshape(y.shape[0], num_heads, -1, 3, y.shape[2] * y.shape[3])
     q, k, v = normalize(y, dim=2).unbind(3)
-    w = torch.einsum("nhcq,nhck->nhqk", q, k / torch.sqrt(torch.tensor(q.shape[2], dtype=q.dtype))).softmax(dim=3)
+    w = torch.einsum("nhcq,nhck->nhqk", q, k / torch.sqrt(torch.tensor(q.shape[2], dtype=q.dtype, device=q.device))).softmax(dim=3)
     y = torch.einsum("nhqk,nhck->nhcq", w, v)
     return mp_conv(y.reshape(*x.shape), sd[prefix + "attn_proj.weight"])
 

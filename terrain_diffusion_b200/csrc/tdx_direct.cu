@@ -601,45 +601,116 @@ __global__ void sched_step_kernel(float* sample, const float* f, float* x0_prev,
   }
 }
 
+// ---- overlap blend / canvas kernels: HBM-bound, one float4 (four pixels of a row) per thread and channel.  Every
+// element still goes through separately rounded __fmul_rn / __fadd_rn / __fdiv_rn in the reference's order, so the
+// vector path is bit-identical to the scalar one (taken when pointers, widths or offsets are not multiples of 4).
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4(float* p, const float4& v) { *reinterpret_cast<float4*>(p) = v; }
+
+template <bool VEC>
 __global__ void blend_accumulate_kernel(float* cval, float* cw, int channels, int CH, int CW, const float* tile,
                                         const float* window, int th, int tw, int y0, int x0) {
-  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  constexpr int V = VEC ? 4 : 1;
+  const int x = (blockIdx.x * blockDim.x + threadIdx.x) * V;
   const int y = blockIdx.y;
   if (x >= tw) return;
   const int Y = y0 + y, X = x0 + x;
-  if (Y < 0 || Y >= CH || X < 0 || X >= CW) return;
-  const float w = window[(size_t)y * tw + x];
-  const size_t cidx = (size_t)Y * CW + X;
-  for (int c = 0; c < channels; ++c) {
-    const float v = __fmul_rn(tile[((size_t)c * th + y) * tw + x], w);
-    cval[(size_t)c * CH * CW + cidx] = __fadd_rn(cval[(size_t)c * CH * CW + cidx], v);
+  if (Y < 0 || Y >= CH) return;
+  if constexpr (VEC) {
+    if (X < 0 || X + 3 >= CW) {           // row segment straddling the canvas edge: element by element
+      for (int i = 0; i < 4; ++i) {
+        if (X + i < 0 || X + i >= CW) continue;
+        const float w = window[(size_t)y * tw + x + i];
+        const size_t ci = (size_t)Y * CW + X + i;
+        for (int c = 0; c < channels; ++c)
+          cval[(size_t)c * CH * CW + ci] = __fadd_rn(cval[(size_t)c * CH * CW + ci],
+                                                     __fmul_rn(tile[((size_t)c * th + y) * tw + x + i], w));
+        cw[ci] = __fadd_rn(cw[ci], w);
+      }
+      return;
+    }
+    const float4 w = ld4(window + (size_t)y * tw + x);
+    const size_t cidx = (size_t)Y * CW + X;
+    for (int c = 0; c < channels; ++c) {
+      const float4 t = ld4(tile + ((size_t)c * th + y) * tw + x);
+      float* d = cval + (size_t)c * CH * CW + cidx;
+      float4 v = ld4(d);
+      v.x = __fadd_rn(v.x, __fmul_rn(t.x, w.x));
+      v.y = __fadd_rn(v.y, __fmul_rn(t.y, w.y));
+      v.z = __fadd_rn(v.z, __fmul_rn(t.z, w.z));
+      v.w = __fadd_rn(v.w, __fmul_rn(t.w, w.w));
+      st4(d, v);
+    }
+    float4 s = ld4(cw + cidx);
+    s.x = __fadd_rn(s.x, w.x); s.y = __fadd_rn(s.y, w.y); s.z = __fadd_rn(s.z, w.z); s.w = __fadd_rn(s.w, w.w);
+    st4(cw + cidx, s);
+  } else {
+    if (X < 0 || X >= CW) return;
+    const float w = window[(size_t)y * tw + x];
+    const size_t cidx = (size_t)Y * CW + X;
+    for (int c = 0; c < channels; ++c) {
+      const float v = __fmul_rn(tile[((size_t)c * th + y) * tw + x], w);
+      cval[(size_t)c * CH * CW + cidx] = __fadd_rn(cval[(size_t)c * CH * CW + cidx], v);
+    }
+    cw[cidx] = __fadd_rn(cw[cidx], w);
   }
-  cw[cidx] = __fadd_rn(cw[cidx], w);
 }
 
+template <bool VEC>
 __global__ void canvas_add_kernel(float* dst, int channels, int DH, int DW, const float* tile, int th, int tw, int y0,
                                   int x0) {
-  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  constexpr int V = VEC ? 4 : 1;
+  const int x = (blockIdx.x * blockDim.x + threadIdx.x) * V;
   const int y = blockIdx.y;
   if (x >= tw) return;
   const int Y = y0 + y, X = x0 + x;
-  if (Y < 0 || Y >= DH || X < 0 || X >= DW) return;
-  for (int c = 0; c < channels; ++c) {
-    const size_t di = ((size_t)c * DH + Y) * DW + X;
-    dst[di] = __fadd_rn(dst[di], tile[((size_t)c * th + y) * tw + x]);
+  if (Y < 0 || Y >= DH) return;
+  if constexpr (VEC) {
+    if (X >= 0 && X + 3 < DW) {
+      for (int c = 0; c < channels; ++c) {
+        float* d = dst + ((size_t)c * DH + Y) * DW + X;
+        const float4 t = ld4(tile + ((size_t)c * th + y) * tw + x);
+        float4 v = ld4(d);
+        v.x = __fadd_rn(v.x, t.x); v.y = __fadd_rn(v.y, t.y); v.z = __fadd_rn(v.z, t.z); v.w = __fadd_rn(v.w, t.w);
+        st4(d, v);
+      }
+      return;
+    }
+  }
+  for (int i = 0; i < V; ++i) {
+    if (X + i < 0 || X + i >= DW) continue;
+    for (int c = 0; c < channels; ++c) {
+      const size_t di = ((size_t)c * DH + Y) * DW + X + i;
+      dst[di] = __fadd_rn(dst[di], tile[((size_t)c * th + y) * tw + x + i]);
+    }
   }
 }
 
+template <bool VEC>
 __global__ void blend_normalize_kernel(float* out, const float* cval, const float* cw, int channels, int64_t plane,
                                        float divisor) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  constexpr int V = VEC ? 4 : 1;
+  int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * V;
   const int64_t n = plane * channels;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x * V;
   for (; i < n; i += stride) {
-    const float q = __fdiv_rn(cval[i], cw[i % plane]);
-    out[i] = divisor == 1.0f ? q : __fdiv_rn(q, divisor);
+    if constexpr (VEC) {
+      const float4 a = ld4(cval + i), w = ld4(cw + i % plane);       // plane % 4 == 0: the four share one channel
+      float4 q;
+      q.x = __fdiv_rn(a.x, w.x); q.y = __fdiv_rn(a.y, w.y); q.z = __fdiv_rn(a.z, w.z); q.w = __fdiv_rn(a.w, w.w);
+      if (divisor != 1.0f) {
+        q.x = __fdiv_rn(q.x, divisor); q.y = __fdiv_rn(q.y, divisor); q.z = __fdiv_rn(q.z, divisor);
+        q.w = __fdiv_rn(q.w, divisor);
+      }
+      st4(out + i, q);
+    } else {
+      const float q = __fdiv_rn(cval[i], cw[i % plane]);
+      out[i] = divisor == 1.0f ? q : __fdiv_rn(q, divisor);
+    }
   }
 }
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 }  // namespace tdx
 
@@ -691,8 +762,17 @@ extern "C" int tdx_blend_accumulate(float* canvas_val, float* canvas_w, int32_t 
   TDX_REQUIRE(channels >= 1 && tile_h >= 1 && tile_w >= 1 && canvas_h >= 1 && canvas_w_px >= 1,
               "blend_accumulate: bad shape");
   dim3 grid((tile_w + 127) / 128, tile_h);
-  blend_accumulate_kernel<<<grid, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      canvas_val, canvas_w, channels, canvas_h, canvas_w_px, tile, window, tile_h, tile_w, y0, x0);
+  const bool vec = (tile_w % 4 == 0) && (canvas_w_px % 4 == 0) && (x0 % 4 == 0) && aligned16(canvas_val) &&
+                   aligned16(canvas_w) && aligned16(tile) && aligned16(window) &&
+                   ((size_t)canvas_h * canvas_w_px) % 4 == 0 && ((size_t)tile_h * tile_w) % 4 == 0;
+  if (vec) {
+    grid.x = (tile_w / 4 + 127) / 128;
+    blend_accumulate_kernel<true><<<grid, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        canvas_val, canvas_w, channels, canvas_h, canvas_w_px, tile, window, tile_h, tile_w, y0, x0);
+  } else {
+    blend_accumulate_kernel<false><<<grid, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        canvas_val, canvas_w, channels, canvas_h, canvas_w_px, tile, window, tile_h, tile_w, y0, x0);
+  }
   TDX_CHECK_CUDA(cudaGetLastError());
   return TDX_OK;
 }
@@ -702,8 +782,16 @@ extern "C" int tdx_canvas_add(float* dst, int32_t channels, int32_t dst_h, int32
   TDX_REQUIRE(dst && tile && channels >= 1 && dst_h >= 1 && dst_w >= 1 && tile_h >= 1 && tile_w >= 1,
               "canvas_add: bad arguments");
   dim3 grid((tile_w + 127) / 128, tile_h);
-  canvas_add_kernel<<<grid, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(dst, channels, dst_h, dst_w, tile,
-                                                                             tile_h, tile_w, y0, x0);
+  const bool vec = (tile_w % 4 == 0) && (dst_w % 4 == 0) && (x0 % 4 == 0) && aligned16(dst) && aligned16(tile) &&
+                   ((size_t)dst_h * dst_w) % 4 == 0 && ((size_t)tile_h * tile_w) % 4 == 0;
+  if (vec) {
+    grid.x = (tile_w / 4 + 127) / 128;
+    canvas_add_kernel<true><<<grid, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(dst, channels, dst_h, dst_w, tile,
+                                                                                     tile_h, tile_w, y0, x0);
+  } else {
+    canvas_add_kernel<false><<<grid, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(dst, channels, dst_h, dst_w, tile,
+                                                                                      tile_h, tile_w, y0, x0);
+  }
   TDX_CHECK_CUDA(cudaGetLastError());
   return TDX_OK;
 }
@@ -712,10 +800,16 @@ extern "C" int tdx_blend_normalize(float* out, const float* canvas_val, const fl
                                    int64_t plane, float divisor, void* stream) {
   TDX_REQUIRE(out && canvas_val && canvas_w && channels >= 1 && plane >= 1, "blend_normalize: bad arguments");
   int64_t n = plane * channels;
-  int blocks = (int)((n + 255) / 256);
+  const bool vec = plane % 4 == 0 && aligned16(out) && aligned16(canvas_val) && aligned16(canvas_w);
+  int blocks = (int)((n / (vec ? 4 : 1) + 255) / 256);
   if (blocks > sm_count() * 8) blocks = sm_count() * 8;
-  blend_normalize_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(out, canvas_val, canvas_w,
-                                                                                    channels, plane, divisor);
+  if (blocks < 1) blocks = 1;
+  if (vec)
+    blend_normalize_kernel<true><<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(out, canvas_val, canvas_w,
+                                                                                            channels, plane, divisor);
+  else
+    blend_normalize_kernel<false><<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(out, canvas_val, canvas_w,
+                                                                                             channels, plane, divisor);
   TDX_CHECK_CUDA(cudaGetLastError());
   return TDX_OK;
 }

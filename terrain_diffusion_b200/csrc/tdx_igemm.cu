@@ -81,6 +81,7 @@ struct IgemmParams {
   int SB;                     // B ring depth
   int b_stage_bytes;          // ncta * 128
   int resident;               // the whole weight set of an item fits the ring: loaded once per CTA, reused by every item
+  int bgroup;                 // taps per weight hand-over group (9, 3 or 1): one full-barrier per group
   int ksplit;                 // split-K: the (chunk, tap) stages of a work item are shared by the ksplit CTAs of a cluster
   float* ws;                  // split-K fp32 partial sums [group][dst part][ksplit-1 sources][ncta/ksplit cols][128 pixels]
   int H, W, nimg, tiles_x, tiles_y, num_items;
@@ -95,6 +96,8 @@ struct IgemmParams {
   int resid_spatial, resid_pnorm;
   float resid_scale, clip;
   TdxOutSpec out[3];
+  float* rms_out;             // optional fp32 [nimg][H][W]: 1 / (eps + rms) of this launch's result
+  const float* resid_inv;     // optional fp32 plane at the residual's resolution: r' = r * resid_inv[pixel]
   int dbg;                    // debug experiment flags (tools/trace_igemm.py), normally 0
   unsigned long long* timeline;  // debug: [2] = {first CTA start, last CTA end} in globaltimer ns, normally null
   unsigned long long* trace;  // debug: per-item phase timestamps of CTA 0 (tools/trace_igemm.py), normally null
@@ -292,19 +295,21 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CU
     if (p.nseg > 1) tma_prefetch_desc(&tm1);
     if (p.nseg > 2) tma_prefetch_desc(&tm2);
   }
-  if (warp == 2 && elect_one()) {
-    for (int i = 0; i < kSA; ++i) {
-      mbar_init(&a_full[i], 1);
-      mbar_init(&a_empty[i], 1);
-    }
-    for (int i = 0; i < p.SB; ++i) {
-      mbar_init(&b_full[i], 1);
-      mbar_init(&b_empty[i], 1);
-    }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&t_full[i], 1);
-      mbar_init(&t_empty[i], kEpiWarps);
-      mbar_init(&x_full[i], p.xsplit > 1 ? (p.xsplit - 1) * 128 : 1);
+  if (warp == 2) {
+    // all 48 barriers at once, two per lane (one thread initialising them in turn costs ~800 cycles of every launch):
+    // [a_full 3][a_empty 3][b_full 18][b_empty 18][t_full 2][t_empty 2][x_full 2], contiguous from `bars`
+    constexpr int kBars = 2 * kSA + 2 * kMaxSB + 6;
+    static_assert(kBars <= 64, "two barriers per lane");
+    const int t_empty0 = 2 * kSA + 2 * kMaxSB + 2;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int i = lane + 32 * k;
+      if (i < kBars) {
+        uint32_t count = 1;
+        if (i >= t_empty0 && i < t_empty0 + 2) count = kEpiWarps;
+        if (i >= t_empty0 + 2) count = p.xsplit > 1 ? (uint32_t)(p.xsplit - 1) * 128u : 1u;
+        mbar_init(&bars[i], count);
+      }
     }
     fence_mbar_init();
   }
@@ -362,19 +367,36 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CU
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
       const uint8_t* bsrc = reinterpret_cast<const uint8_t*>(p.B) +
                             ((size_t)split * p.stages_per_item + st0) * p.b_stage_bytes;
-      for (int ks = 0; ks < st1 - st0; ++ks) {
-        if (!p.resident) mbar_wait(&b_empty[sb], ph ^ 1, 200 + sb);
-        if (elect_one()) {
-          if (p.dbg & 2) {
-            mbar_arrive(&b_full[sb]);
-          } else {
-            mbar_expect_tx(&b_full[sb], p.b_stage_bytes);
-            bulk_load_1d(bsrc + (size_t)ks * p.b_stage_bytes, &b_full[sb], b_ring + sb * p.b_stage_bytes,
-                         p.b_stage_bytes);
+      // The stages are handed over in GROUPS of up to `bgroup` consecutive taps of one 64-channel chunk: a group
+      // completes ONE barrier, the one of its first slot, so the issuer waits once per group instead of once per 4
+      // MMAs (an mbarrier try_wait costs ~90 cycles even when the phase is already complete).  bgroup = 9 when the
+      // ring holds two chunks or the whole weight slice, 1 (stage by stage) for shorter, streaming rings.
+      int ks = 0;
+      for (int s = st0; s < st1;) {
+        int seg, ch, tap0, taps;
+        stage_locate(p, s, seg, ch, tap0, taps);
+        const int nt = (taps - tap0 < st1 - s) ? taps - tap0 : st1 - s;
+        int head = sb, gi = 0;
+        for (int t = 0; t < nt; ++t) {
+          if (!p.resident) mbar_wait(&b_empty[sb], ph ^ 1, 200 + sb);
+          const bool first = gi == 0;                        // first stage of a hand-over group: its barrier carries the group
+          if (++gi == p.bgroup) gi = 0;                      // (no integer division in this loop: ~150 cycles each)
+          if (first) head = sb;
+          if (elect_one()) {
+            uint64_t* full = &b_full[head];
+            if (p.dbg & 2) {
+              if (first) mbar_arrive(full);
+            } else {
+              if (first) mbar_expect_tx(full, (uint32_t)(nt - t < p.bgroup ? nt - t : p.bgroup) * p.b_stage_bytes);
+              bulk_load_1d(bsrc + (size_t)(ks + t) * p.b_stage_bytes, full, b_ring + sb * p.b_stage_bytes,
+                           p.b_stage_bytes);
+            }
           }
+          __syncwarp();
+          if (++sb == p.SB) { sb = 0; ph ^= 1; }
         }
-        __syncwarp();
-        if (++sb == p.SB) { sb = 0; ph ^= 1; }
+        ks += nt;
+        s += nt;
       }
       if (p.resident) break;   // the ring now holds this CTA's whole weight slice for every later item
     }
@@ -402,8 +424,10 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CU
     const uint32_t tmem_u = uni(tmem_base);
     const uint32_t SBu = uni((uint32_t)p.SB);
     const uint32_t resident = uni((uint32_t)p.resident);
+    const uint32_t bgroup = uni((uint32_t)p.bgroup);
     uint32_t sa = uni(0), sb = uni(0);
-    uint32_t pha = 0, phb = 0;
+    uint32_t pha = 0;
+    uint32_t fmask = uni(0);   // expected parity of every b_full barrier (a group's barrier = its first slot's)
     uint32_t it = uni(0);
     int s0, s1;
     {
@@ -433,44 +457,39 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CU
         if (lane == 0 && s == s0) TDX_TRACE(2, it);
         s += tap1 - tap0;
         const uint32_t a_lo = a_lo0 + sa * (kAStageBytes >> 4);
-        if (steady && taps == 9 && tap0 == 0 && tap1 == 9) {
-          // ---- 36 MMAs back to back (resident ring: SB == stages_per_item, a chunk's 9 stages never wrap)
-          const uint32_t b_lo = b_lo0 + sb * b_stage16;
+        const uint32_t nt = (uint32_t)(tap1 - tap0);
+        // tap offsets (r * 10 + c pixels) come from a packed table, 5 bits per tap; a 1x1 segment reads the patch centre
+        const unsigned long long taptab = taps == 9 ? (0x16ad18b50820ull >> (5 * tap0)) : (unsigned long long)(kPatchW + 1);
+        // ---- hand-over groups of up to `bgroup` taps (one group = everything when the weights are already resident)
+        const uint32_t gsz = steady ? nt : bgroup;
+        unsigned long long tt = taptab;
+        for (uint32_t g0 = 0; g0 < nt; g0 += gsz) {
+          const uint32_t gn = nt - g0 < gsz ? nt - g0 : gsz;
+          if (!steady) {
+            mbar_wait(&b_full[sb], (fmask >> sb) & 1u, 500 + sb);
+            tc_fence_after();
+            fmask ^= 1u << sb;
+          }
           if (elect_one()) {
-            uint32_t bl = b_lo;
+            uint32_t slot = sb, bl = b_lo0 + sb * b_stage16;
+            unsigned long long t2 = tt;
 #pragma unroll 1
-            for (int tap = 0; tap < 9; ++tap, bl += b_stage16) {
-              const uint32_t al = a_lo + (uint32_t)((0x16ad18b50820ull >> (5 * tap)) & 31ull);
+            for (uint32_t t = 0; t < gn; ++t, t2 >>= 5) {
+              const uint32_t al = a_lo + (uint32_t)(t2 & 31ull);
 #pragma unroll
               for (int j = 0; j < 4; ++j)
                 umma_bf16(d_tmem, pack_desc(al + j * a_kstep16, a_h), pack_desc(bl + j * b_kstep16, b_h), idesc,
-                          (accumulate | tap | j) ? 1u : 0u);
+                          (accumulate | t | j) ? 1u : 0u);
+              if (!resident) umma_commit(&b_empty[slot]);
+              bl += b_stage16;
+              if (++slot == SBu) { slot = 0; bl = b_lo0; }
             }
           }
           __syncwarp();
           accumulate = 1;
-          sb += 9;
-          if (sb >= SBu) { sb -= SBu; phb ^= 1; }
-        } else {
-          for (int tap = tap0; tap < tap1; ++tap) {
-            // tap offset (r * 10 + c pixels) from a packed table: 5 bits per tap; a 1x1 segment reads the patch centre
-            const uint32_t tapoff = taps == 9 ? (uint32_t)((0x16ad18b50820ull >> (5 * tap)) & 31ull) : (uint32_t)(kPatchW + 1);
-            const uint32_t b_lo = b_lo0 + sb * b_stage16;
-            if (!steady) {
-              mbar_wait(&b_full[sb], phb, 500 + sb);
-              tc_fence_after();
-            }
-            if (elect_one()) {
-#pragma unroll
-              for (int j = 0; j < 4; ++j)
-                umma_bf16(d_tmem, pack_desc(a_lo + tapoff + j * a_kstep16, a_h), pack_desc(b_lo + j * b_kstep16, b_h),
-                          idesc, (accumulate | j) ? 1u : 0u);
-              if (!resident) umma_commit(&b_empty[sb]);
-            }
-            __syncwarp();
-            accumulate = 1;
-            if (++sb == SBu) { sb = 0; phb ^= 1; }
-          }
+          tt >>= 5 * gn;
+          sb += gn;
+          if (sb >= SBu) sb -= SBu;
         }
         if (elect_one()) umma_commit(&a_empty[sa]);
         __syncwarp();
@@ -494,7 +513,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CU
     const int y = m >> 3, x = m & 7;
     const int C8 = p.cout >> 3;
     const bool need_norm = (p.epi & TDX_EPI_PNORM) || p.out[0].kind == TDX_OUT_PNORM_SILU ||
-                           p.out[1].kind == TDX_OUT_PNORM_SILU || p.out[2].kind == TDX_OUT_PNORM_SILU;
+                           p.out[1].kind == TDX_OUT_PNORM_SILU || p.out[2].kind == TDX_OUT_PNORM_SILU ||
+                           p.rms_out != nullptr;
     const uint32_t my_rank = p.cluster_stats ? cluster_ctarank() : 0;
     TileWalk tw;
     tw.init(p);
@@ -524,10 +544,18 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CU
     const int rsp = p.resid_spatial == TDX_SP_UP2 ? TDX_SP_DOWN2 : (p.resid_spatial == TDX_SP_DOWN2 ? TDX_SP_UP2 : TDX_SP_SAME);
     uint4 upre[4], rpre[kGroups];
     const uint4* rbase_pre = nullptr;
+    float rinv_pre = 1.f;
     auto resid_fetch = [&](const TileWalk& t) {
       const int Y_ = t.ty * kTileH + y, X_ = t.tx * kTileW + x;
       const bool vld = (Y_ < p.H) && (X_ < p.W);
       rbase_pre = p.resid + pixel_off_at(rsp, t.img, Y_, X_);
+      if (p.resid_inv) {
+        // the producer of the residual left 1 / (eps + rms) per pixel: one float instead of all Cout channels
+        const uint32_t po = rsp == TDX_SP_DOWN2 ? (uint32_t)t.img * (plane >> 2) + (uint32_t)((Y_ >> 1) * (p.W >> 1) + (X_ >> 1))
+                          : rsp == TDX_SP_UP2 ? (uint32_t)t.img * (plane << 2) + (uint32_t)((Y_ << 1) * (p.W << 1) + (X_ << 1))
+                                              : (uint32_t)t.img * plane + (uint32_t)(Y_ * p.W + X_);
+        rinv_pre = vld ? __ldg(p.resid_inv + po) : 0.f;
+      }
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int g = wq * 2 + (j >> 1) * 2 * kWQ + (j & 1);
@@ -589,7 +617,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CU
         float rscale = p.resid_scale;
         if (has_resid) resid_fetch(tw);   // issued before the accumulator wait: overlaps the MMAs of this item
         const uint4* rbase = rbase_pre;
-        if (has_resid && p.resid_pnorm && !(p.dbg & 32)) {
+        if (has_resid && p.resid_inv) {
+          rscale = p.resid_scale * rinv_pre;
+        } else if (has_resid && p.resid_pnorm && !(p.dbg & 32)) {
           // the residual's pixel-norm runs over ALL Cout channels: the kWQ warps of a pixel quadrant each read their
           // share of the 8-channel planes (C8 is a multiple of 8) and combine through shared memory
           float ss = 0.f;
@@ -739,7 +769,11 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CU
                 emit_v(ck, v, inv);
               }
             }
-            if (pass == 0) inv = finish_norm(sumsq);
+            if (pass == 0) {
+              inv = finish_norm(sumsq);
+              if (p.rms_out && wq == 0 && kpart == 0 && tw.split == 0 && valid)
+                p.rms_out[(uint32_t)img * plane + (uint32_t)(Y * p.W + X)] = inv;
+            }
           }
         }
       }
@@ -785,6 +819,7 @@ int igemm_prepare() {
 
 static bool needs_norm(const TdxIgemmDesc& d) {
   if (d.epi_flags & TDX_EPI_PNORM) return true;
+  if (d.rms_out) return true;
   for (int o = 0; o < 3; ++o)
     if (d.out[o].kind == TDX_OUT_PNORM_SILU) return true;
   return false;
@@ -844,13 +879,14 @@ static int max_active_clusters(int csize) {
 //   * pixel-norm layers exchange statistics inside a cluster, so all nsplit*ks CTAs of an M tile share one (<= 8).
 struct ItemShape { int ncta, resident, sb, ksplit; };
 
-static ItemShape choose_item_shape(int cout, int tiles, int stages, int chunks, int forced_n, bool norm) {
+static ItemShape choose_item_shape(int cout, int tiles, int stages, int chunks, int forced_n, bool norm,
+                                   int want_k = 0) {
   if (!forced_n && getenv("TDX_IGEMM_N")) forced_n = atoi(getenv("TDX_IGEMM_N"));
   if (forced_n && (forced_n > cout || cout % forced_n)) forced_n = 0;
-  const int forced_k = getenv("TDX_IGEMM_KSPLIT") ? atoi(getenv("TDX_IGEMM_KSPLIT")) : 0;
+  const int forced_k = want_k > 0 ? want_k : (getenv("TDX_IGEMM_KSPLIT") ? atoi(getenv("TDX_IGEMM_KSPLIT")) : 0);
   const int ring_budget = kSmemBudget - kSA * kAStageBytes - kSmemMisc;
   double best = 1e30;
-  ItemShape bs = {64, 0, 2, 1};
+  ItemShape bs = {64, 0, 2, want_k > 0 ? 0 : 1};   // ksplit 0 = "the requested split is not possible"
   for (int n = 64; n <= 256 && n <= cout; n += 64) {
     if (cout % n) continue;
     if (forced_n && n != forced_n) continue;
@@ -890,6 +926,7 @@ static ItemShape choose_item_shape(int cout, int tiles, int stages, int chunks, 
       if (l2 > t) t = l2;
       if (per_sm > t) t = per_sm;
       t += epi + red;
+      if (want_k > 0 && ks != want_k) continue;
       if (forced_k > 1 && ks == 1) t *= 1e6;   // debug override: take the forced split whenever it is valid
       if (t < best) { best = t; bs = {n, resident, sb, ks}; }
     }
@@ -919,10 +956,15 @@ int igemm_launch(const TdxIgemmDesc& d, const CUtensorMap* tms, cudaStream_t str
   p.tiles_y = (d.height + kTileH - 1) / kTileH;
   const int tiles = p.tiles_x * p.tiles_y * d.n_img;
   const bool norm = needs_norm(d);
-  const ItemShape shp = choose_item_shape(d.c_out, tiles, p.stages_per_item, chunks, d.n_per_item, norm);
+  const ItemShape shp = choose_item_shape(d.c_out, tiles, p.stages_per_item, chunks, d.n_per_item, norm, d.k_split);
+  TDX_REQUIRE(shp.ksplit >= 1, "igemm: k_split=%d is not possible for this launch (n_per_item=%d)", d.k_split,
+              d.n_per_item);
   p.ncta = shp.ncta;
   p.resident = shp.resident;
   p.SB = shp.sb;
+  // streaming rings stay stage by stage: a grouped hand-over makes the issuer wait for a group's LAST stage, which
+  // costs latency slack exactly where the weight stream is L2-bound (measured: N=128 layers 5-25 % slower)
+  p.bgroup = (shp.resident || shp.sb >= 18) ? 9 : 1;
   p.ksplit = shp.ksplit;
   p.nsplit = d.c_out / p.ncta;
   p.b_stage_bytes = p.ncta * 128;
@@ -942,6 +984,8 @@ int igemm_launch(const TdxIgemmDesc& d, const CUtensorMap* tms, cudaStream_t str
   p.resid_scale = d.resid_scale;
   p.clip = d.clip;
   for (int o = 0; o < 3; ++o) p.out[o] = d.out[o];
+  p.rms_out = d.rms_out;
+  p.resid_inv = d.resid_inv;
   p.trace = g_trace_ptr;
   p.dbg = g_dbg_flags;
   p.timeline = (g_timeline_ptr && g_timeline_idx < g_timeline_cap) ? g_timeline_ptr + 2 * (g_timeline_idx++) : nullptr;
@@ -1006,6 +1050,9 @@ int igemm_validate(const TdxIgemmDesc& d) {
   TDX_REQUIRE(d.n_img >= 1 && d.height >= 8 && d.width >= 8 && d.height % 8 == 0 && d.width % 8 == 0,
               "igemm: bad shape n=%d h=%d w=%d (h, w multiples of 8)", d.n_img, d.height, d.width);
   if (d.epi_flags & TDX_EPI_EMB_SILU) TDX_REQUIRE(d.cvec != nullptr, "igemm: EMB_SILU needs cvec");
+  if (d.resid_inv)
+    TDX_REQUIRE((d.epi_flags & TDX_EPI_RESID) && !d.resid_pnorm,
+                "igemm: resid_inv needs TDX_EPI_RESID and resid_pnorm == 0 (it replaces the recomputed pixel-norm)");
   if (d.epi_flags & TDX_EPI_RESID) {
     TDX_REQUIRE(d.resid != nullptr, "igemm: RESID needs resid");
     if (d.resid_spatial == TDX_SP_UP2)

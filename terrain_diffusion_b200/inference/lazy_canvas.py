@@ -10,11 +10,12 @@ engine (`infinite_tensor>=0.3.0`, requirements.txt:32; absent from /root/referen
 
 PARITY UNPINNED against the library itself (it is not on disk and the reference has no tests for it); the semantics
 above are pinned by tests/test_lazy_canvas_gpu.py against a brute-force evaluation, and the arithmetic (fp32 sums in
-row-major window order) by the bounded-canvas tests.  Everything stays in HBM: blocks of the canvas are fp32 CUDA
-tensors, windows are added with tdx_canvas_add.
+row-major window order) by the bounded-canvas tests.  Everything stays in HBM: every computed window is an fp32 CUDA tile
+(byte-limited LRU, recompute on miss), a slice is assembled by adding its windows with tdx_canvas_add.
 """
 from __future__ import annotations
 
+from collections import OrderedDict
 from dataclasses import dataclass
 
 import torch
@@ -31,8 +32,14 @@ class TensorWindow:
 
 
 class LazyCanvas:
+    """cache_limit (bytes, None = unbounded): the computed windows are kept as fp32 tiles in HBM, least recently used
+    first out, like the reference's `MemoryTileStore(cache_size_bytes)` (world_pipeline.py:666-674); a window that was
+    evicted is simply recomputed by `f` the next time a slice needs it (f is deterministic: tile-seeded noise).  The
+    cache is trimmed after a request has been served, so a limit smaller than one request's windows only means that
+    the oldest of them are not kept."""
+
     def __init__(self, channels: int, f, output_window: TensorWindow, device, args=(), args_windows=(),
-                 batch_size: int | None = None, block: int = 512):
+                 batch_size: int | None = None, block: int = 512, cache_limit: int | None = None):
         self.channels = channels
         self.f = f
         self.win = output_window
@@ -42,32 +49,42 @@ class LazyCanvas:
         self.args, self.args_windows = tuple(args), tuple(args_windows)
         assert len(self.args) == len(self.args_windows)
         self.batch_size = batch_size
-        self.block = block
-        self.blocks: dict = {}
-        self.done: set = set()
+        self.block = block                      # kept for API compatibility (storage is per window now)
+        self.cache_limit = None if cache_limit is None else int(cache_limit)
+        self.tiles: OrderedDict = OrderedDict()  # (i, j) -> fp32 [C, h, w] window output, in LRU order
+        self.cache_bytes = 0
         self.windows_computed = 0
+        self.windows_evicted = 0
 
     # ------------------------------------------------------------------ storage
-    def _block(self, by, bx):
-        key = (by, bx)
-        if key not in self.blocks:
-            self.blocks[key] = torch.zeros((self.channels, self.block, self.block), dtype=torch.float32,
-                                           device=self.device)
-        return self.blocks[key]
+    @property
+    def done(self):
+        """Window indices currently cached."""
+        return self.tiles.keys()
 
-    def _add(self, tile: torch.Tensor, y0: int, x0: int):
-        c, th, tw = tile.shape
-        tile = tile.contiguous()
-        b = self.block
-        for by in range(y0 // b, (y0 + th - 1) // b + 1):
-            for bx in range(x0 // b, (x0 + tw - 1) // b + 1):
-                blk = self._block(by, bx)
-                L.call(L.lib().tdx_canvas_add, blk.device, blk.data_ptr(), c, b, b, tile.data_ptr(), th, tw, y0 - by * b,
-                       x0 - bx * b)
+    def _store(self, ij, tile: torch.Tensor):
+        tile = tile.to(self.device, torch.float32).contiguous()
+        assert tuple(tile.shape) == tuple(self.win.size), (tuple(tile.shape), self.win.size)
+        self.tiles[ij] = tile
+        self.cache_bytes += tile.numel() * 4
+        self.windows_computed += 1
+
+    def _evict(self, protect=()):
+        if self.cache_limit is None:
+            return
+        protect = set(protect)
+        for ij in list(self.tiles.keys()):
+            if self.cache_bytes <= self.cache_limit:
+                break
+            if ij in protect:
+                continue
+            t = self.tiles.pop(ij)
+            self.cache_bytes -= t.numel() * 4
+            self.windows_evicted += 1
 
     def clear_cache(self):
-        self.blocks.clear()
-        self.done.clear()
+        self.tiles.clear()
+        self.cache_bytes = 0
 
     # ------------------------------------------------------------------ windows
     def window_origin(self, i: int, j: int) -> tuple[int, int]:
@@ -88,25 +105,20 @@ class LazyCanvas:
         return out
 
     def _ensure(self, idxs):
-        missing = [ij for ij in idxs if ij not in self.done]
+        missing = [ij for ij in idxs if ij not in self.tiles]
         if not missing:
             return
         if self.batch_size is None:
             for (i, j) in missing:
-                tile = self.f((0, i, j), *self._dep_slices(i, j))
-                self._add(tile.to(self.device, torch.float32), *self.window_origin(i, j))
-                self.done.add((i, j))
-                self.windows_computed += 1
+                self._store((i, j), self.f((0, i, j), *self._dep_slices(i, j)))
         else:
             for g0 in range(0, len(missing), self.batch_size):
                 grp = missing[g0:g0 + self.batch_size]
                 deps = [self._dep_slices(i, j) for (i, j) in grp]
                 lists = [list(col) for col in zip(*deps)] if deps and deps[0] else []
                 tiles = self.f([(0, i, j) for (i, j) in grp], *lists)
-                for (i, j), tile in zip(grp, tiles):
-                    self._add(tile.to(self.device, torch.float32), *self.window_origin(i, j))
-                    self.done.add((i, j))
-                    self.windows_computed += 1
+                for ij, tile in zip(grp, tiles):
+                    self._store(ij, tile)
 
     # ------------------------------------------------------------------ read
     def __getitem__(self, key) -> torch.Tensor:
@@ -116,15 +128,17 @@ class LazyCanvas:
         a, b, c, d = ys.start, ys.stop, xs.start, xs.stop
         if None in (a, b, c, d) or b <= a or d <= c:
             raise IndexError("row and column slices need explicit start < stop (world coordinates, may be negative)")
-        self._ensure(self.windows_for(a, b, c, d))
+        idxs = self.windows_for(a, b, c, d)
+        self._ensure(idxs)
+        # the slice = sum of the covering windows in row-major window order (the order of the bounded samplers and of
+        # oracle/tiling.py), whatever the order they were computed in: reads are reproducible bit for bit
         out = torch.zeros((self.channels, b - a, d - c), dtype=torch.float32, device=self.device)
-        blk = self.block
-        for by in range(a // blk, (b - 1) // blk + 1):
-            for bx in range(c // blk, (d - 1) // blk + 1):
-                if (by, bx) not in self.blocks:
-                    continue
-                y0, y1 = max(a, by * blk), min(b, (by + 1) * blk)
-                x0, x1 = max(c, bx * blk), min(d, (bx + 1) * blk)
-                out[:, y0 - a:y1 - a, x0 - c:x1 - c] = self.blocks[(by, bx)][:, y0 - by * blk:y1 - by * blk,
-                                                                               x0 - bx * blk:x1 - bx * blk]
+        _, th, tw = self.win.size
+        for (i, j) in idxs:
+            tile = self.tiles[(i, j)]
+            self.tiles.move_to_end((i, j))
+            y0, x0 = self.window_origin(i, j)
+            L.call(L.lib().tdx_canvas_add, self.device, out.data_ptr(), self.channels, b - a, d - c, tile.data_ptr(),
+                   th, tw, y0 - a, x0 - c)
+        self._evict()          # trim to the limit: the windows just used are the most recent, the oldest go first
         return out[cs]

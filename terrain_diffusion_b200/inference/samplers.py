@@ -28,19 +28,20 @@ def _solve_cache(model):
     return model._solve_cache
 
 
-def get_diffusion_solve(model, scheduler, n, h, w, num_steps) -> DiffusionSolve:
-    """Cached fused N-step solve.  The key is everything the solve bakes in: the sigma table and the per-step order
-    schedule (they cover sigma_min/max/rho/schedule, scaling_p/scaling_t, lower_order_final, euler_at_final, ...) plus
-    the options that change the update formula.  The caller's scheduler is put in the state the reference leaves it in
-    (`set_timesteps(num_steps)`) on a cache hit too."""
+def get_diffusion_solve(model, scheduler, n, h, w, num_steps, step_range=None) -> DiffusionSolve:
+    """Cached fused N-step solve (or one phase of it: step_range).  The key is everything the solve bakes in: the
+    sigma table and the per-step order schedule (they cover sigma_min/max/rho/schedule, scaling_p/scaling_t,
+    lower_order_final, euler_at_final, ...) plus the options that change the update formula.  The caller's scheduler
+    is put in the state the reference leaves it in (`set_timesteps(num_steps)`) on a cache hit too."""
     scheduler.set_timesteps(num_steps)
     c = scheduler.config
-    key = (n, h, w, num_steps, tuple(float(v) for v in scheduler.sigmas), tuple(scheduler.order_schedule()),
+    key = (n, h, w, num_steps, None if step_range is None else tuple(int(v) for v in step_range),
+           tuple(float(v) for v in scheduler.sigmas), tuple(scheduler.order_schedule()),
            float(c.sigma_data), c.prediction_type, c.final_sigmas_type, c.solver_order, c.algorithm_type, c.solver_type,
            id(model.folded()))
     cache = _solve_cache(model)
     if key not in cache:
-        cache[key] = DiffusionSolve(model, scheduler, n, h, w, num_steps)
+        cache[key] = DiffusionSolve(model, scheduler, n, h, w, num_steps, step_range=step_range)
     return cache[key]
 
 
@@ -145,5 +146,7 @@ def sample_decoder_diffusion_sharded(model, scheduler, cond_img: torch.Tensor, n
         out = solve.run(x, cd)
         for t, (i0, j0) in enumerate(chunk):
             canvas.add_tile(out[t].clone(), i0, j0)
+        if g0 + len(chunk) >= canvas.n_boundary_tiles():
+            canvas.start_exchange()          # boundary rows are done: their strip travels during the interior solves
     canvas.finalize()
     return canvas.normalized_owned(), (canvas.own_lo, canvas.own_hi)

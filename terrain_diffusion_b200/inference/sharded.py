@@ -8,8 +8,14 @@ The (sum x*w, sum w) partial sums of that strip go to the neighbour with one poi
 
 Bit-exactness: fp32 addition is order dependent, and the single-GPU order is row-major over tiles.  A
 rank therefore first INSTALLS the strip it receives from its upper neighbour and only then accumulates its own tiles
-in row-major order, so every pixel sees exactly the single-GPU sequence of additions.  The U-Net solves (the expensive
-part) are not serialised by this: tiles are solved first and buffered, `finalize()` runs the cheap blend chain.
+in row-major order, so every pixel sees exactly the single-GPU sequence of additions.
+
+Overlap: the strip a rank sends only holds contributions of its OWN overhanging tile rows (the constructor rejects
+partitions in which a strip could reach past the next rank), so nothing chains from rank to rank.  `my_tiles()` lists
+the overhanging (boundary) tile rows FIRST; as soon as they are solved, `start_exchange()` blends them into a separate
+strip canvas, and posts the send to the lower neighbour together with the receive from the upper one (one batched
+isend/irecv, NCCL's own stream) -- the transfer runs while the interior tiles are being solved, and `finalize()` only
+waits for it before the (cheap) blend of the rank's own rows.
 """
 from __future__ import annotations
 
@@ -40,14 +46,28 @@ class ShardedCanvas:
         self.cover_hi = min(height, self.row_starts[self.rows[-1]] + tile_size)   # how far this rank's tiles reach
         if self.rank + 1 < self.world and self.cover_hi > self.bounds[self.rank + 2]:
             raise ValueError("stripes are thinner than the tile overhang; use fewer ranks for this canvas")
-        # local canvas covers [own_lo, cover_hi)
+        # local canvas covers [own_lo, cover_hi) (the rows past own_hi are scratch: the neighbour owns them)
         self.local = canvas_factory(channels, self.cover_hi - self.own_lo, width, self.device,
                                     origin=(self.own_lo, 0))
+        self._factory = canvas_factory
         self._tiles: list = []
+        self._work, self._recv_buf, self._send_buf = None, None, None
+
+    def boundary_rows(self) -> list[int]:
+        """Tile rows of this rank whose tiles overhang into the next rank's pixel rows."""
+        if self.rank + 1 >= self.world:
+            return []
+        return [r for r in self.rows if self.row_starts[r] + self.tile > self.own_hi]
 
     def my_tiles(self) -> list[tuple[int, int]]:
-        """Tile origins this rank must solve, row-major."""
-        return [(self.row_starts[r], j0) for r in self.rows for j0 in self.col_starts]
+        """Tile origins this rank must solve: the boundary rows first (their strip can then travel while the interior
+        is being solved), each group row-major."""
+        brows = self.boundary_rows()
+        order = brows + [r for r in self.rows if r not in brows]
+        return [(self.row_starts[r], j0) for r in order for j0 in self.col_starts]
+
+    def n_boundary_tiles(self) -> int:
+        return len(self.boundary_rows()) * len(self.col_starts)
 
     def add_tile(self, tile: torch.Tensor, i0: int, j0: int) -> None:
         self._tiles.append((tile, i0, j0))
@@ -55,26 +75,47 @@ class ShardedCanvas:
     def _strip_rows(self) -> int:
         return max(0, self.cover_hi - self.own_hi)
 
+    def _upper_rows(self) -> int:
+        if self.rank == 0:
+            return 0
+        upper_cover = min(self.height,
+                          self.row_starts[shard_rows(len(self.row_starts), self.world, self.rank - 1)[-1]] + self.tile)
+        return max(0, upper_cover - self.own_lo)
+
+    def start_exchange(self) -> None:
+        """Call once every boundary tile has been added (any time later is also correct, just less overlapped)."""
+        if self._work is not None or self.world == 1:
+            return
+        ops = []
+        n_up = self._upper_rows()
+        if n_up > 0:
+            self._recv_buf = torch.empty((self.channels + 1, n_up, self.width), dtype=torch.float32,
+                                         device=self.device)
+            ops.append(dist.P2POp(dist.irecv, self._recv_buf, self._global(self.rank - 1), self.group))
+        n = self._strip_rows()
+        if self.rank + 1 < self.world and n > 0:
+            # the overhang only ever holds this rank's own boundary tiles: blend them (row-major) in a strip canvas
+            strip = self._factory(self.channels, n, self.width, self.device, origin=(self.own_hi, 0))
+            for tile, i0, j0 in sorted(self._tiles, key=lambda t: (t[1], t[2])):
+                if i0 + self.tile > self.own_hi:
+                    strip.accumulate(tile, i0, j0)
+            self._send_buf = torch.cat([strip.val, strip.wsum[None]], dim=0).contiguous()
+            ops.append(dist.P2POp(dist.isend, self._send_buf, self._global(self.rank + 1), self.group))
+        self._work = dist.batch_isend_irecv(ops) if ops else []
+
     def finalize(self) -> None:
-        """Blend chain: install the upper neighbour's strip, accumulate own tiles (row-major), pass the overhang on."""
-        if self.rank > 0:
-            upper_cover = min(self.height,
-                              self.row_starts[shard_rows(len(self.row_starts), self.world, self.rank - 1)[-1]]
-                              + self.tile)
-            n = max(0, upper_cover - self.own_lo)
-            if n > 0:
-                buf = torch.empty((self.channels + 1, n, self.width), dtype=torch.float32, device=self.device)
-                dist.recv(buf, src=self._global(self.rank - 1), group=self.group)
-                self.local.val[:, :n] = buf[:-1]
-                self.local.wsum[:n] = buf[-1]
+        """Wait for the strips, install the upper neighbour's, accumulate the own tiles (row-major)."""
+        self.start_exchange()
+        for w in (self._work or []):
+            w.wait()
+        if self._recv_buf is not None:
+            n = self._recv_buf.shape[1]
+            self.local.val[:, :n] = self._recv_buf[:-1]
+            self.local.wsum[:n] = self._recv_buf[-1]
         for tile, i0, j0 in sorted(self._tiles, key=lambda t: (t[1], t[2])):
             self.local.accumulate(tile, i0, j0)
         self._tiles.clear()
-        n = self._strip_rows()
-        if self.rank + 1 < self.world and n > 0:
-            lo = self.own_hi - self.own_lo
-            buf = torch.cat([self.local.val[:, lo:lo + n], self.local.wsum[None, lo:lo + n]], dim=0).contiguous()
-            dist.send(buf, dst=self._global(self.rank + 1), group=self.group)
+        self._work, self._recv_buf, self._send_buf = None, None, None
 
     def _global(self, r: int) -> int:
         return dist.get_global_rank(self.group, r) if self.group is not None else r

@@ -16,15 +16,24 @@ from ..models.plan import UNetEmitter, UNetProgram
 class DiffusionSolve:
     """K-step EDM DPM-Solver++ solve of `n` independent tiles: sample[n, Cs, h, w] (<- noise*sigma0), cond[n, Cc, h, w]."""
 
-    def __init__(self, model, scheduler, n: int, h: int, w: int, num_steps: int):
+    def __init__(self, model, scheduler, n: int, h: int, w: int, num_steps: int, step_range=None):
+        """step_range = (i0, i1): only steps i0 .. i1-1 of the `num_steps` schedule (one PHASE of a multi-phase
+        InfiniteDiffusion solve, inference/multiphase.py).  A range that starts in the middle of the schedule starts
+        from a blended canvas, so the multistep history is empty there: its first step is first order, exactly like
+        a scheduler whose state was reset and positioned at step i0."""
         fw = model.folded()
         dev = fw.device
+        scheduler.set_timesteps(num_steps)
+        order = scheduler.order_schedule()
+        i0, i1 = (0, num_steps) if step_range is None else (int(step_range[0]), int(step_range[1]))
+        if not (0 <= i0 < i1 <= num_steps):
+            raise ValueError(f"step_range {step_range} is not inside the {num_steps}-step schedule")
+        self.schedule_steps, self.step_range = num_steps, (i0, i1)
+        co = [scheduler.step_coefficients(i, order[i] and not (i == i0 and i0 > 0)) for i in range(i0, i1)]
+        num_steps = i1 - i0                      # from here on: the number of steps this solve runs
         self.model, self.n, self.h, self.w, self.num_steps = model, n, h, w, num_steps
         cs = fw.out_channels
         cc = fw.in_channels - cs
-        scheduler.set_timesteps(num_steps)
-        order = scheduler.order_schedule()
-        co = [scheduler.step_coefficients(i, order[i]) for i in range(num_steps)]
         self.coef = torch.tensor([[c["c_skip"], c["c_out"], c["r"], c["k"]] for c in co], dtype=torch.float64).to(
             torch.float32).to(dev).contiguous()
         self.c_in = torch.tensor([c["c_in"] for c in co], dtype=torch.float64).to(torch.float32).to(dev).contiguous()

@@ -29,6 +29,26 @@ from .. import _lib as L
 from ..layout import pack_weight_segments
 
 
+_TUNED = None
+_TUNED_NEW: dict = {}      # shapes measured in this process (TDX_AUTOTUNE=1); tools/tune_igemm.py writes them out
+TUNED_PATH = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tuned_shapes.json")
+
+
+def tuned_shapes() -> dict:
+    """{"cout|n|h|w|segments|norm": [n_per_item, k_split]} measured on a B200 (tools/tune_igemm.py)."""
+    global _TUNED
+    if _TUNED is None:
+        _TUNED = {}
+        if os.environ.get("TDX_TUNED_TABLE", "1") != "0":
+            try:
+                import json
+                with open(TUNED_PATH) as f:
+                    _TUNED = dict(json.load(f).get("shapes", {}))
+            except Exception:
+                _TUNED = {}
+    return _TUNED
+
+
 def effective_weight(w: torch.Tensor, gain=1.0) -> torch.Tensor:
     """fp32 weight MPConv.forward convolves with (mp_layers.py:203-213): global-RMS normalise, gain / sqrt(fan_in)."""
     w = w.detach().to(torch.float32)
@@ -316,6 +336,13 @@ class UNetEmitter:
             res["act"] = self.act(stage_key + ".act", c, hh, ww)
             self._set_out(desc, slot, res["act"], kind, spatial, scale)
             slot += 1
+            if kind == L.OUT_PNORM_SILU and hasattr(desc, "rms_out"):
+                # the consumer block adds pixelnorm(raw) as its residual: leave it the per-pixel factor (fp32 plane)
+                key = stage_key + ".inv"
+                if key not in self.arena:
+                    self.arena[key] = torch.empty((self.n, h, w), dtype=torch.float32, device=self.dev)
+                res["inv"] = self.arena[key]
+                desc.rms_out = res["inv"].data_ptr()
         if enc_index is not None and enc_index in self.fw.skip_consumer:
             d = self.fw.skip_consumer[enc_index]
             cx = d["cin"] - d["skip_channels"]
@@ -337,6 +364,7 @@ class UNetEmitter:
         d.b_packed = self.fw.packed(wkey, n_item).data_ptr()
         d.c_out = cout
         d.n_img, d.height, d.width = self.n, h, w
+        d._wkey = wkey          # (python-side attribute) lets _add_igemm re-pack for the tuned work-item width
         return d
 
     def _finish_block(self, prog, d, b, key, cout, h, w, nxt, enc_index):
@@ -378,9 +406,72 @@ class UNetEmitter:
         return cur
 
     def _add_igemm(self, prog, d):
+        self._apply_tuned_shape(d)
         L.check(L.lib().tdx_program_add_igemm(prog.handle, C.byref(d)))
         prog.n_igemm += 1
         prog.n_launch += 1
+
+    # ------------------------------------------------------------------ measured (n_per_item, k_split) per launch shape
+    @staticmethod
+    def _shape_key(d) -> str:
+        norm = bool(d.epi_flags & L.EPI_PNORM) or bool(d.rms_out) or any(d.out[o].kind == L.OUT_PNORM_SILU
+                                                                        for o in range(3))
+        segs = ";".join(f"{d.a_channels[i]}x{d.a_taps[i]}" for i in range(d.n_seg))
+        return f"{d.c_out}|{d.n_img}|{d.height}|{d.width}|{segs}|{int(norm)}"
+
+    def _apply_tuned_shape(self, d):
+        """Work-item width N and split-K factor of this launch: from the measured table (tuned_shapes.json, produced on
+        a B200 by tools/tune_igemm.py: the library's cost model is only the fallback), or measured now when
+        TDX_AUTOTUNE=1.  The table is a file, not a run-time search, so every process / rank makes the same choice and
+        multi-GPU results stay bit-identical to single-GPU ones."""
+        wkey = getattr(d, "_wkey", None)
+        if wkey is None:
+            return
+        key = self._shape_key(d)
+        choice = tuned_shapes().get(key)
+        if choice is None and os.environ.get("TDX_AUTOTUNE") == "1":
+            choice = self._measure_shape(d, wkey)
+            tuned_shapes()[key] = choice
+            _TUNED_NEW[key] = choice
+        if choice is None:
+            return
+        n_item, ks = int(choice[0]), int(choice[1])
+        if d.c_out % n_item:
+            return
+        d.n_per_item = n_item
+        d.b_packed = self.fw.packed(wkey, n_item).data_ptr()
+        d.k_split = ks
+
+    def _measure_shape(self, d, wkey):
+        """Time every valid (N, k_split) of this launch: median of 5 x 12 back-to-back dependent launches each."""
+        lib = L.lib()
+        best, best_t = None, float("inf")
+        keep = (d.n_per_item, d.b_packed, d.k_split)
+        with torch.cuda.device(self.dev):
+            stream = L.current_stream_ptr(self.dev)
+            for n_item in (64, 128, 192, 256):
+                if d.c_out % n_item or n_item > d.c_out:
+                    continue
+                d.n_per_item = n_item
+                d.b_packed = self.fw.packed(wkey, n_item).data_ptr()
+                for ks in (1, 2, 3, 4, 6, 8):
+                    d.k_split = ks
+                    if lib.tdx_igemm_run(C.byref(d), stream) != 0:
+                        continue
+                    ts = []
+                    for _ in range(5):
+                        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        e0.record()
+                        for _ in range(12):
+                            lib.tdx_igemm_run(C.byref(d), stream)
+                        e1.record()
+                        torch.cuda.synchronize()
+                        ts.append(e0.elapsed_time(e1))
+                    t = sorted(ts)[len(ts) // 2]
+                    if t < best_t:
+                        best, best_t = (n_item, ks), t
+        d.n_per_item, d.b_packed, d.k_split = keep
+        return list(best) if best else None
 
     # ------------------------------------------------------------------ embedding / modulation vectors
     def emit_embed(self, prog: UNetProgram, labels=None, emb_in=None):
@@ -486,9 +577,12 @@ class UNetEmitter:
                     self._set_out(d, 0, xn, L.OUT_RAW)
                     self._set_out(d, 1, a_in, L.OUT_SILU, L.SP_SAME, 1.0)
                     self._add_igemm(prog, d)
-                    resid, resid_pn = xn, 0
+                    resid, resid_pn, resid_inv = xn, 0, None
                 else:
                     a_in, resid, resid_pn = cur["act"], cur["raw"], 1
+                    resid_inv = cur.get("inv")
+                    if resid_inv is not None:
+                        resid_pn = 0
                 hbuf = self.act(key + "h", cout, h, w)
                 d = self._igemm(prog, [(a_in, cout, 9)], key + "res0", cout, h, w)
                 d.epi_flags = L.EPI_EMB_SILU
@@ -500,6 +594,8 @@ class UNetEmitter:
                 d.resid = resid.data_ptr()
                 d.resid_spatial = resid_sp
                 d.resid_pnorm = resid_pn
+                if resid_inv is not None:
+                    d.resid_inv = resid_inv.data_ptr()
                 d.resid_scale = fw.w_skip
                 cur = self._finish_block(prog, d, b, key, cout, h, w, nxt, enc_index)
             else:

@@ -42,14 +42,40 @@ def test_lazy_canvas_equals_bruteforce_window_sum_incl_negative_coordinates(size
     for k, (a, b, c, d) in enumerate([(-70, 95, -130, 20), (0, 64, 0, 64), (100, 101, -3, 300)]):
         got = cv[:, a:b, c:d].cpu()
         want = _brute(a, b, c, d, 3, size, stride, off)
-        if k == 0:
-            assert torch.equal(got, want), (a, b, c, d)   # same (row-major) order of fp32 additions: bit-identical
-        else:
-            # windows cached by earlier requests were added in THAT request's order: equal up to fp32 re-association
-            assert torch.allclose(got, want, rtol=0, atol=2e-6), (a, b, c, d)
+        # every read sums its windows in row-major order, whatever order they were computed in: bit-identical
+        assert torch.equal(got, want), (k, a, b, c, d)
     n = len(calls)
     cv[:, 0:64, 0:64]                      # cached: no window is computed twice
     assert len(calls) == n and len(set(calls)) == n
+
+
+def test_cache_limit_evicts_least_recently_used_windows_and_recomputes_them():
+    """Byte-limited window cache (the reference's MemoryTileStore(cache_size_bytes), world_pipeline.py:666-674): HBM use
+    stays bounded while exploring, evicted windows are recomputed on the next request, results do not change."""
+    calls = []
+
+    def f(ctx):
+        calls.append(ctx)
+        return _tile(ctx[1], ctx[2], 2, 32).cuda()
+
+    tile_bytes = 2 * 32 * 32 * 4
+    cv = LazyCanvas(2, f, TensorWindow((2, 32, 32), (2, 24, 24)), "cuda", cache_limit=6 * tile_bytes)
+    n_win = len(cv.windows_for(0, 60, 0, 60))             # window indices -1..2 per axis: 16 windows > the limit of 6
+    assert n_win == 16
+    first = cv[:, 0:60, 0:60].cpu()
+    assert torch.equal(first, _brute(0, 60, 0, 60, 2, 32, 24, 0))
+    assert cv.cache_bytes <= 6 * tile_bytes and cv.windows_evicted == n_win - 6 and len(cv.done) == 6
+    n = len(calls)
+    for k in range(8):                                    # walk away: memory stays bounded
+        a = 200 * (k + 1)
+        assert torch.equal(cv[:, a:a + 40, -a:-a + 40].cpu(), _brute(a, a + 40, -a, -a + 40, 2, 32, 24, 0))
+        assert cv.cache_bytes <= 6 * tile_bytes
+    again = cv[:, 0:60, 0:60].cpu()                       # everything was evicted meanwhile: recomputed, same values
+    assert torch.equal(again, first)
+    assert len(calls) >= n + n_win
+    unbounded = LazyCanvas(2, f, TensorWindow((2, 32, 32), (2, 24, 24)), "cuda")
+    unbounded[:, 0:60, 0:60]
+    assert unbounded.windows_evicted == 0 and len(unbounded.done) == n_win
 
 
 def test_dependency_windows_use_the_same_window_index_and_batches():

@@ -26,9 +26,10 @@ class CpuCanvas:
         t = tile.shape[-1]
         win = otile.linear_weight_window(t)
         y, x = y0 - self.origin[0], x0 - self.origin[1]
+        lo = max(0, -y)                                    # rows above this canvas are clipped (strip canvases)
         h = min(t, self.val.shape[1] - y)
-        self.val[:, y:y + h, x:x + t] += (tile * win)[:, :h]
-        self.wsum[y:y + h, x:x + t] += win[:h]
+        self.val[:, y + lo:y + h, x:x + t] += (tile * win)[:, lo:h]
+        self.wsum[y + lo:y + h, x:x + t] += win[lo:h]
 
 
 def _tile_value(i0, j0, c, t):
@@ -42,8 +43,12 @@ def _worker(rank, world, port, h, w, t, stride, c, out_path):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         cv = ShardedCanvas(c, h, w, t, stride, "cpu", canvas_factory=CpuCanvas)
-        for (i0, j0) in cv.my_tiles():
+        tiles = cv.my_tiles()
+        assert tiles[:cv.n_boundary_tiles()] == [ij for ij in sorted(tiles) if ij[0] + t > cv.own_hi and rank + 1 < world]
+        for k, (i0, j0) in enumerate(tiles):
             cv.add_tile(_tile_value(i0, j0, c, t), i0, j0)
+            if k + 1 == cv.n_boundary_tiles():
+                cv.start_exchange()                       # strips travel while the interior tiles are "solved"
         cv.finalize()
         full = cv.gather(0)
         if rank == 0:

@@ -25,7 +25,7 @@ def main():
     m.load_state_dict(O.procedural_state_dict(cfg, seed=0))
     m = m.to(dev)
     g = torch.Generator().manual_seed(3)
-    h = w = 64 + 48 * 3
+    h = w = 64 + 48 * 7          # 8 tile rows: stripes of 4 (2 ranks) or 2 (4 ranks) rows
     noise = (torch.randn(1, 1, h, w, generator=g) * 80).to(dev)
     cond = torch.randn(1, 4, h, w, generator=g).to(dev)
     own, (lo, hi) = sample_decoder_diffusion_sharded(m, EDMDPMSolverMultistepScheduler(), cond, noise, 64, 48,
