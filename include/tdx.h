@@ -214,6 +214,22 @@ int tdx_blend_normalize(float* out, const float* canvas_val, const float* canvas
                         float divisor, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
+ * Elementwise glue of the consistency stages (WorldPipeline._latent_inference / _decoder_inference,
+ * inference/world_pipeline.py:1052-1131,1209-1242); the U-Net and the TrigFlow update s' = cos t*x_t - sin t*sigma_d*pred
+ * run as a one-step program whose last convolution applies the update (tdx_conv_out_run coefficients
+ * {cos t, sin t*sigma_d, 0, 0}).
+ * ------------------------------------------------------------------------------------------------------------------ */
+/* x_t = a*sample + b*noise (world_pipeline.py:1097-1098,1235: a = cos t, b = sin t*sigma_data); sample may be NULL (0). */
+int tdx_trig_mix(float* out, const float* sample, const float* noise, int64_t numel, float a, float b, void* stream);
+/* out[n][c] = x[n][c]*scale*w, out[n][C] = w: the packed window output cat([x*w, w]) (world_pipeline.py:1130,1242). */
+int tdx_pack_weighted(float* out, const float* x, const float* w, int32_t n_img, int32_t channels, int64_t plane,
+                      float scale, void* stream);
+/* cond[n][c] = nearest_upsample(packed[n][c] / packed[n][last], factor) for c < keep: normalise-on-read of a packed
+ * window + F.interpolate(mode='nearest') (world_pipeline.py:1223-1226). */
+int tdx_window_to_cond(float* out, const float* packed, int32_t n_img, int32_t packed_channels, int32_t keep, int32_t h,
+                       int32_t w, int32_t factor, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
  * Elevation read-out (WorldPipeline._compute_elev, inference/world_pipeline.py:1277-1313): the reference normalises
  * the canvases on read and runs data/laplacian_encoder.py (torchvision resize + gaussian_blur) on the CPU for every
  * get().  These five fp32 primitives keep it on the device; terrain_diffusion_b200/inference/postproc.py composes them

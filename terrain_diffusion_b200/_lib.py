@@ -126,6 +126,14 @@ def _declare(l: C.CDLL) -> None:
     l.tdx_blend_normalize.restype = C.c_int
     l.tdx_blend_normalize.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_float,
                                       C.c_void_p]
+    l.tdx_trig_mix.restype = C.c_int
+    l.tdx_trig_mix.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_float, C.c_void_p]
+    l.tdx_pack_weighted.restype = C.c_int
+    l.tdx_pack_weighted.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_float,
+                                    C.c_void_p]
+    l.tdx_window_to_cond.restype = C.c_int
+    l.tdx_window_to_cond.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                     C.c_int32, C.c_void_p]
     l.tdx_post_normalize.restype = C.c_int
     l.tdx_post_normalize.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int32, C.c_float,
                                      C.c_float, C.c_void_p]

@@ -45,6 +45,18 @@ def get_diffusion_solve(model, scheduler, n, h, w, num_steps, step_range=None) -
     return cache[key]
 
 
+def get_consistency_solve(model, n, h, w, t: float, sigma_data: float = 0.5, from_unit_noise: bool = False,
+                          out_scale: float = 1.0) -> DiffusionSolve:
+    """Cached one-step TrigFlow consistency program (solve.consistency_rows) for `n` tiles of h x w."""
+    from .solve import consistency_rows
+    key = ("cm", n, h, w, float(t), float(sigma_data), bool(from_unit_noise), float(out_scale), id(model.folded()))
+    cache = _solve_cache(model)
+    if key not in cache:
+        cache[key] = DiffusionSolve(model, None, n, h, w, 1,
+                                    coef_rows=consistency_rows(t, sigma_data, from_unit_noise, out_scale))
+    return cache[key]
+
+
 @torch.no_grad()
 def sample_decoder_diffusion_tiled(model, scheduler, cond_img: torch.Tensor, noise: torch.Tensor,
                                    tile_size: Optional[int] = None, tile_stride: Optional[int] = None, *,

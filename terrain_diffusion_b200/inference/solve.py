@@ -16,21 +16,28 @@ from ..models.plan import UNetEmitter, UNetProgram
 class DiffusionSolve:
     """K-step EDM DPM-Solver++ solve of `n` independent tiles: sample[n, Cs, h, w] (<- noise*sigma0), cond[n, Cc, h, w]."""
 
-    def __init__(self, model, scheduler, n: int, h: int, w: int, num_steps: int, step_range=None):
-        """step_range = (i0, i1): only steps i0 .. i1-1 of the `num_steps` schedule (one PHASE of a multi-phase
+    def __init__(self, model, scheduler, n: int, h: int, w: int, num_steps: int, step_range=None, coef_rows=None):
+        """coef_rows: explicit per-step tables [dict(c_in, t, c_skip, c_out, r, k)] instead of a scheduler's (the
+        TrigFlow consistency step is the same fused program with other numbers: consistency_rows()).
+        step_range = (i0, i1): only steps i0 .. i1-1 of the `num_steps` schedule (one PHASE of a multi-phase
         InfiniteDiffusion solve, inference/multiphase.py).  A range that starts in the middle of the schedule starts
         from a blended canvas, so the multistep history is empty there: its first step is first order, exactly like
         a scheduler whose state was reset and positioned at step i0."""
         fw = model.folded()
         dev = fw.device
-        scheduler.set_timesteps(num_steps)
-        order = scheduler.order_schedule()
-        i0, i1 = (0, num_steps) if step_range is None else (int(step_range[0]), int(step_range[1]))
-        if not (0 <= i0 < i1 <= num_steps):
-            raise ValueError(f"step_range {step_range} is not inside the {num_steps}-step schedule")
-        self.schedule_steps, self.step_range = num_steps, (i0, i1)
-        co = [scheduler.step_coefficients(i, order[i] and not (i == i0 and i0 > 0)) for i in range(i0, i1)]
-        num_steps = i1 - i0                      # from here on: the number of steps this solve runs
+        if coef_rows is not None:
+            co = [dict(r) for r in coef_rows]
+            self.schedule_steps, self.step_range = len(co), (0, len(co))
+            num_steps = len(co)
+        else:
+            scheduler.set_timesteps(num_steps)
+            order = scheduler.order_schedule()
+            i0, i1 = (0, num_steps) if step_range is None else (int(step_range[0]), int(step_range[1]))
+            if not (0 <= i0 < i1 <= num_steps):
+                raise ValueError(f"step_range {step_range} is not inside the {num_steps}-step schedule")
+            self.schedule_steps, self.step_range = num_steps, (i0, i1)
+            co = [scheduler.step_coefficients(i, order[i] and not (i == i0 and i0 > 0)) for i in range(i0, i1)]
+            num_steps = i1 - i0                  # from here on: the number of steps this solve runs
         self.model, self.n, self.h, self.w, self.num_steps = model, n, h, w, num_steps
         cs = fw.out_channels
         cc = fw.in_channels - cs
@@ -67,12 +74,26 @@ class DiffusionSolve:
         """noise: [n, Cs, h, w] initial sample (already scaled by sigma_0); returns the denoised sample (a view of the
         solver's state buffer -- copy it before the next run)."""
         if self.host_emb:
-            embs = [self.model._host_embedding(self.labels[i], conditional_inputs or [])
-                    for i in range(self.num_steps)]
-            self.emb_all.copy_(torch.cat(embs, dim=0))
+            # conditional models: ONE batched evaluation of compute_embeddings for the labels of all steps
+            ci = [c.to(self.labels.device).repeat(self.num_steps, *([1] * (c.dim() - 1)))
+                  for c in (conditional_inputs or [])]
+            self.emb_all.copy_(self.model._host_embedding(self.labels.reshape(-1), ci))
         self.sample.copy_(noise)
         if cond is not None:
             self.cond.copy_(cond)
         self.x0_prev.zero_()
         self.prog.run(use_graph)
         return self.sample
+
+
+def consistency_rows(t: float, sigma_data: float = 0.5, from_unit_noise: bool = False, out_scale: float = 1.0):
+    """Coefficient row that makes the fused step program a TrigFlow consistency step
+    (world_pipeline.py:1097-1128,1235-1239):   model_in = x_t / sigma_d ;  s' = cos t * x_t + sin t * sigma_d * F
+    (pred = -F).  from_unit_noise: the sample buffer holds the unit-variance noise z of a FIRST phase (s = 0, so
+    x_t = sin t * sigma_d * z): the re-noising folds into the scalars and no mixing launch is needed.  out_scale
+    multiplies the result (1 / sigma_d for a final phase)."""
+    import math
+    ct, st = math.cos(t), math.sin(t)
+    s = st * sigma_data if from_unit_noise else 1.0
+    return [dict(c_in=s / sigma_data, t=float(t), c_skip=ct * s * out_scale, c_out=st * sigma_data * out_scale, r=0.0,
+                 k=0.0)]

@@ -204,21 +204,23 @@ class EDMUnet2D(nn.Module):
 
     # ------------------------------------------------------------------ embeddings (conditional models: host side)
     def _host_embedding(self, noise_labels, conditional_inputs):
-        """compute_embeddings (edm_unet.py:145-159) in fp32 torch ops on the model's device (tiny GEMVs)."""
-        from .plan import effective_weight
+        """compute_embeddings (edm_unet.py:145-159) for conditional models: a handful of fp32 GEMVs on the model's
+        device with the weights folded once (FoldedWeights); rows = noise_labels.numel() (all the steps of a solve in
+        one call)."""
+        g = self.folded().g
         embeds = []
         if self.noise_linear is not None:
-            pe = self.noise_fourier(noise_labels.float())
-            embeds.append(pe @ effective_weight(self.noise_linear.weight).T)
-        for layer, kind, inp in zip(self.conditional_layers, self._cond_kinds, conditional_inputs):
+            embeds.append(self.noise_fourier(noise_labels.float()) @ g["noise_linear"])
+        for i, (layer, kind, inp) in enumerate(zip(self.conditional_layers, self._cond_kinds, conditional_inputs)):
             if kind == "float":
-                embeds.append(layer[0](inp.float()) @ effective_weight(layer[1].weight).T)
+                embeds.append(layer[0](inp.float()) @ g[f"cond{i}"])
             elif kind == "tensor":
-                embeds.append(_host_mp_silu(inp.float() @ effective_weight(layer.weight).T))
+                embeds.append(_host_mp_silu(inp.float() @ g[f"cond{i}"]))
             else:
-                embeds.append(torch.nn.functional.embedding(inp, layer.weight.float()))
-        w = torch.tensor(self.conditional_weights, dtype=torch.float32, device=embeds[0].device)
-        emb = sum(e * wi for e, wi in zip(embeds, w)) / torch.linalg.vector_norm(w)
+                embeds.append(torch.nn.functional.embedding(inp, g[f"cond{i}"]))
+        w = self.conditional_weights
+        w32 = torch.tensor([float(v) for v in w], dtype=torch.float32)            # host: mp_sum's weights and their norm
+        emb = sum(e * float(wi) for e, wi in zip(embeds, w32)) / float(torch.linalg.vector_norm(w32))
         return _host_mp_silu(emb)
 
     # ------------------------------------------------------------------ forward

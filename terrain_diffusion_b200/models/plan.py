@@ -169,6 +169,14 @@ class FoldedWeights:
             g["noise_linear"] = effective_weight(sd["noise_linear.weight"]).t().contiguous()  # [in][out]
             if self.pos_emb:
                 g["noise_freqs"] = sd["noise_fourier.freqs"].contiguous()
+        # conditional-input layers of compute_embeddings (edm_unet.py:145-159): folded once like everything else
+        for i, (kind, _dim, _wgt) in enumerate(cfg.get("conditional_inputs") or []):
+            if kind == "float":
+                g[f"cond{i}"] = effective_weight(sd[f"conditional_layers.{i}.1.weight"]).t().contiguous()
+            elif kind == "tensor":
+                g[f"cond{i}"] = effective_weight(sd[f"conditional_layers.{i}.weight"]).t().contiguous()
+            else:
+                g[f"cond{i}"] = sd[f"conditional_layers.{i}.weight"].contiguous()      # MPEmbedding: un-normalised table
         first = enc[0]
         w_in = effective_weight(sd[f"enc.{first['name']}.weight"])               # [cout][ci][3][3]
         g["conv_in"] = w_in.permute(2, 3, 1, 0).reshape(9, w_in.shape[1], w_in.shape[0]).contiguous()  # [tap][ci][cout]

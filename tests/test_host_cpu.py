@@ -189,3 +189,25 @@ def test_latent_stage_seed_offsets_match_the_reference_call_sites():
     offs = [int(v) for v in g["latent_seed_offsets"]]
     assert offs == [5819, 5820]
     assert [pipeline.LATENT_INIT_SEED_OFFSET, pipeline.LATENT_STEP_SEED_OFFSET] == offs
+
+
+def test_integration_md_ctypes_stub_matches_the_library_abi(tmp_path):
+    """the binding printed in INTEGRATION.md must be the real ABI.  The python block is taken FROM THE
+    DOCUMENT TEXT, pointed at the built library and executed: its struct sizes must equal tdx_abi_sizeof (the stub
+    asserts that itself) and its field list must be the header's."""
+    import re
+    from pathlib import Path
+    from terrain_diffusion_b200 import _lib as L
+    text = (Path(__file__).resolve().parent.parent / "INTEGRATION.md").read_text()
+    blocks = re.findall(r"```python\n(.*?)```", text, flags=re.S)
+    stub = next(b for b in blocks if "class TdxIgemmDesc" in b)
+    stub = stub.replace('C.CDLL("libtdx.so")', f'C.CDLL({str(L.LIB_PATH)!r})')
+    ns: dict = {}
+    exec(compile(stub, "INTEGRATION.md", "exec"), ns)           # runs the stub's own sizeof assertion
+    doc_fields = [f[0] for f in ns["TdxIgemmDesc"]._fields_]
+    assert doc_fields == [f[0] for f in L.TdxIgemmDesc._fields_]
+    assert C.sizeof(ns["TdxIgemmDesc"]) == C.sizeof(L.TdxIgemmDesc) == L.lib().tdx_abi_sizeof(1)
+    header = (Path(__file__).resolve().parent.parent / "include" / "tdx.h").read_text()
+    body = header[header.index("typedef struct TdxIgemmDesc {"):header.index("} TdxIgemmDesc;")]
+    for name in doc_fields:
+        assert re.search(r"\b" + re.escape(name) + r"\b", body), name

@@ -132,3 +132,48 @@ def test_three_stage_pipeline_slice_equals_direct_stage_evaluation():
     assert pipe.coarse.windows_computed >= 1 and pipe.latents_init.windows_computed > pipe.latents.windows_computed
     n = pipe.residual_normalized(40, -20, 90, 70)
     assert torch.isfinite(n).all()
+
+
+def test_world_pipeline_drop_in_surface_from_pretrained_to_bind_get(tmp_path):
+    """SURVEY 8(b) Pipeline row: WorldPipeline.from_pretrained(path, seed=..., latents_batch_size=..., torch_compile=...,
+    dtype=..., cache_limit=..., **kw).to(device).bind() -- the call chain of api.py:37-52 / tiff_export.py:95-139 /
+    latency.py:39-94 -- then .get() -> CPU tensors and .residual / .latents / .coarse -> un-normalised CPU fp32 windows
+    (negative indices legal), equal to the device-resident TerrainPipeline with the same seed."""
+    from terrain_diffusion_b200.inference import WorldPipeline
+
+    def build(cfg):
+        m = EDMUnet2D(**cfg).eval()
+        m.load_state_dict(ounet.procedural_state_dict(cfg, seed=0))
+        return m
+
+    def cond_fn(i1, i2, j1, j2):
+        gg = torch.Generator().manual_seed(i1 * 7919 + j1 + 12345)
+        return torch.randn(5, i2 - i1, j2 - j1, generator=gg)
+
+    kw = dict(decoder_tile_size=128, decoder_tile_stride=96, residual_mean=0.1, residual_std=1.2)
+    src = WorldPipeline.from_local_models(build(COARSE_CFG), build(BASE_CFG), build(ounet.DECODER_CFG), seed=5, **kw)
+    src.save_pretrained(tmp_path)
+    assert (tmp_path / "config.json").exists() and (tmp_path / "base_model" / "config.json").exists()
+    world = WorldPipeline.from_pretrained(str(tmp_path), seed=11, latents_batch_size=[1, 2, 4, 8, 16],
+                                          torch_compile=True, dtype="bf16", caching_strategy="direct",
+                                          cache_limit=64 << 20, conditioning_fn=cond_fn)
+    assert world.seed == 11 and world.decoder_tile_size == 128 and world.residual is None
+    world = world.to("cuda").bind(hdf5_file=None)
+    assert world.device.type == "cuda"
+    out = world.get(-30, 10, 34, 106, with_climate=True)
+    assert out["elev"].device.type == "cpu" and out["elev"].shape == (64, 96) and out["elev"].dtype == torch.float32
+    assert out["climate"].device.type == "cpu" and out["climate"].shape == (5, 64, 96)
+    assert torch.isfinite(out["elev"]).all() and torch.isfinite(out["climate"]).all()
+    r = world.residual[:, -30:34, 10:106]
+    assert r.device.type == "cpu" and r.shape == (2, 64, 96) and float(r[1].min()) > 0
+    assert world.latents[:, -4:4, 0:12].shape == (6, 8, 12) and world.coarse[:, 0:2, -1:1].shape == (7, 2, 2)
+    # same seed, device-resident variant: identical windows
+    ref = TerrainPipeline(world.coarse_model, world.base_model, world.decoder_model, seed=11, conditioning_fn=cond_fn,
+                          coarse_means=world.kwargs["coarse_means"], coarse_stds=world.kwargs["coarse_stds"],
+                          cond_snr=world.kwargs["cond_snr"], histogram_raw=world.kwargs["histogram_raw"],
+                          latents_means=world.cond_input_mean, latents_stds=world.cond_input_std,
+                          decoder_tile_size=128, decoder_tile_stride=96, residual_mean=0.1, residual_std=1.2)
+    assert torch.equal(ref.residual[:, -30:34, 10:106].cpu(), r)
+    assert world.change_seed(12) is True and len(world._residual.done) == 0
+    with pytest.raises(NotImplementedError):
+        WorldPipeline(caching_strategy="indirect").from_local_models(None, None, None, caching_strategy="indirect").bind("TEMP")

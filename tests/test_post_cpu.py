@@ -100,7 +100,8 @@ def test_pipeline_get_wires_the_read_out_like_the_reference(monkeypatch):
     monkeypatch.setattr(H, "compute_elev", fake_elev)
     monkeypatch.setattr(H, "compute_climate", fake_climate)
     p = object.__new__(TerrainPipeline)
-    p.residual, p.latents, p.coarse, p.lc = "R", "L", "C", 8
+    p._residual, p._latents, p._coarse, p.lc = "R", "L", "C", 8
+    p._host_views = False
     p.residual_mean, p.residual_std = None, None
     with pytest.raises(ValueError):
         p.get_elev(0, 0, 8, 8)
@@ -123,7 +124,7 @@ def test_pipeline_small_api_mirrors_world_pipeline(monkeypatch):
     from terrain_diffusion_b200.inference.noise import next_seed
 
     class RecCanvas:
-        def __init__(self, channels, f, win, dev, args=(), args_windows=(), batch_size=None):
+        def __init__(self, channels, f, win, dev, args=(), args_windows=(), batch_size=None, cache_limit=None):
             self.f, self.done = f, set()
 
         def clear_cache(self):
@@ -134,9 +135,11 @@ def test_pipeline_small_api_mirrors_world_pipeline(monkeypatch):
     monkeypatch.setattr(PL, "linear_weight_window", lambda size, dev: torch.zeros(size, size))
     monkeypatch.setattr(PL, "coarse_stage_tile", lambda *a: seen.setdefault("coarse", a))
     dummy = SimpleNamespace(device=torch.device("cpu"))
-    p = PL.TerrainPipeline(dummy, dummy, dummy, 2 ** 64 + 7, lambda *a: "SMAP", coarse_means=[0.0] * 6,
+    smap = torch.arange(5 * 64 * 64, dtype=torch.float32).view(5, 64, 64)
+    p = PL.TerrainPipeline(dummy, dummy, dummy, 2 ** 64 + 7, lambda i1, i2, j1, j2: smap[:, :i2 - i1, :j2 - j1],
+                           coarse_means=[0.0] * 6,
                            coarse_stds=[1.0] * 6, cond_snr=[0.5, 0.4, 0.3, 0.2, 0.1], histogram_raw=[0.0] * 5,
-                           latents_means=[0.0] * 5, latents_stds=[1.0] * 5, residual_mean=0.1, residual_std=1.2)
+                           latents_means=[0.0] * 7, latents_stds=[1.0] * 7, residual_mean=0.1, residual_std=1.2)
     assert p.seed == 7 and p.native_resolution == 90.0
     assert p.change_seed(7) is False and p.change_seed(2 ** 64 + 9) is True and p.seed == 9
     p.coarse.done.add((0, 0))
@@ -151,11 +154,20 @@ def test_pipeline_small_api_mirrors_world_pipeline(monkeypatch):
     # the coarse stage callback picks up the CURRENT seed and conditioning (world_pipeline.py:909-959)
     p.coarse.f((0, 2, -1))
     args = seen["coarse"]
-    assert args[2] == p.seed and args[3] == (0, 2, -1) and args[4] == "SMAP" and args[5] is p._t_cond
+    assert args[2] == p.seed and args[3] == (0, 2, -1) and torch.equal(args[4], smap) and args[5] is p._t_cond
     assert args[6] is p._cond_inputs
     with p as q:
         q.latents_init.done.add((3, 3))
     assert not p.latents_init.done
+    # imported rasters overlay the injected conditioning map (set_custom_conditioning_import, world_pipeline.py:781-819)
+    p.residual.done.add((5, 5))
+    p.set_custom_conditioning_import(2, np.full((3, 4), 7.0, np.float32), 10, -2, default_value=-1.0)
+    assert not p.residual.done                                         # rebuild() dropped the cache
+    m = p._conditioning_model_input(8, 16, -4, 4)
+    assert m.shape == (5, 8, 8) and torch.equal(m[0], smap[0, :8, :8])
+    assert float(m[2, 2, 2]) == 7.0 and float(m[2, 4, 5]) == 7.0 and float(m[2, 5, 2]) == -1.0 and float(m[2, 0, 0]) == -1.0
+    with pytest.raises(ValueError):
+        p.set_custom_conditioning_import(7, np.zeros((2, 2)), 0, 0)
     # portable_rng.next_seed known answers (computed with the reference: parents 1, 42, 2^63+12345, 2^64-1)
     assert [next_seed(s) for s in (1, 42, 2 ** 63 + 12345, 0xFFFFFFFFFFFFFFFF)] == [
         14210067475669473140, 1039766031909981117, 1104045458667958325, 13583675427266712300]
