@@ -371,6 +371,25 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CU
       // completes ONE barrier, the one of its first slot, so the issuer waits once per group instead of once per 4
       // MMAs (an mbarrier try_wait costs ~90 cycles even when the phase is already complete).  bgroup = 9 when the
       // ring holds two chunks or the whole weight slice, 1 (stage by stage) for shorter, streaming rings.
+      if (p.bgroup == 1) {
+        // stage-by-stage hand-over (streaming rings): the tightest loop possible -- at N >= 128 this warp has to issue a
+        // stage every ~256 cycles, and an mbarrier try_wait alone costs ~90
+        for (int ks = 0; ks < st1 - st0; ++ks) {
+          mbar_wait(&b_empty[sb], ph ^ 1, 200 + sb);
+          if (elect_one()) {
+            if (p.dbg & 2) {
+              mbar_arrive(&b_full[sb]);
+            } else {
+              mbar_expect_tx(&b_full[sb], p.b_stage_bytes);
+              bulk_load_1d(bsrc + (size_t)ks * p.b_stage_bytes, &b_full[sb], b_ring + sb * p.b_stage_bytes,
+                           p.b_stage_bytes);
+            }
+          }
+          __syncwarp();
+          if (++sb == p.SB) { sb = 0; ph ^= 1; }
+        }
+        continue;
+      }
       int ks = 0;
       for (int s = st0; s < st1;) {
         int seg, ch, tap0, taps;
@@ -907,7 +926,7 @@ static ItemShape choose_item_shape(int cout, int tiles, int stages, int chunks, 
       const int resident = (ks == 1 && stages * stage_bytes <= ring_budget && stages <= kMaxSB) ? 1 : 0;
       int sb = resident ? stages : ring_budget / stage_bytes;
       if (sb > kMaxSB) sb = kMaxSB;
-      if (sb < 2) continue;
+      if (sb < 2 && !resident) continue;
       int grid = items * ks < sm_count() ? (int)(items * ks) : sm_count();
       grid -= grid % (nsplit * ks);
       if (grid <= 0) continue;

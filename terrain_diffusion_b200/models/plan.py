@@ -31,6 +31,7 @@ from ..layout import pack_weight_segments
 
 _TUNED = None
 _TUNED_NEW: dict = {}      # shapes measured in this process (TDX_AUTOTUNE=1); tools/tune_igemm.py writes them out
+_TUNE_CANDIDATES: dict = {}   # TDX_AUTOTUNE=2: valid (N, k_split) per shape key, in program order
 TUNED_PATH = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tuned_shapes.json")
 
 
@@ -437,10 +438,13 @@ class UNetEmitter:
             return
         key = self._shape_key(d)
         choice = tuned_shapes().get(key)
+        if os.environ.get("TDX_AUTOTUNE") == "2" and key not in _TUNE_CANDIDATES:
+            _TUNE_CANDIDATES[key] = self._valid_shapes(d, wkey)       # tools/tune_igemm.py graph mode
         if choice is None and os.environ.get("TDX_AUTOTUNE") == "1":
             choice = self._measure_shape(d, wkey)
-            tuned_shapes()[key] = choice
-            _TUNED_NEW[key] = choice
+            if choice is not None:
+                tuned_shapes()[key] = choice
+                _TUNED_NEW[key] = choice
         if choice is None:
             return
         n_item, ks = int(choice[0]), int(choice[1])
@@ -449,6 +453,26 @@ class UNetEmitter:
         d.n_per_item = n_item
         d.b_packed = self.fw.packed(wkey, n_item).data_ptr()
         d.k_split = ks
+
+    def _valid_shapes(self, d, wkey):
+        """Every (N, k_split) this launch accepts (one trial launch each)."""
+        lib = L.lib()
+        out = []
+        keep = (d.n_per_item, d.b_packed, d.k_split)
+        with torch.cuda.device(self.dev):
+            stream = L.current_stream_ptr(self.dev)
+            for n_item in (64, 128, 192, 256):
+                if d.c_out % n_item or n_item > d.c_out:
+                    continue
+                d.n_per_item = n_item
+                d.b_packed = self.fw.packed(wkey, n_item).data_ptr()
+                for ks in (1, 2, 3, 4, 6, 8):
+                    d.k_split = ks
+                    if lib.tdx_igemm_run(C.byref(d), stream) == 0:
+                        out.append([n_item, ks])
+            torch.cuda.synchronize()
+        d.n_per_item, d.b_packed, d.k_split = keep
+        return out
 
     def _measure_shape(self, d, wkey):
         """Time every valid (N, k_split) of this launch: median of 5 x 12 back-to-back dependent launches each."""

@@ -149,19 +149,16 @@ class EDMDPMSolverMultistepScheduler:
         return self.precondition_inputs(sample, self.sigmas[self._step_index])
 
     def index_for_timestep(self, timestep, schedule_timesteps=None):
-        st = self.timesteps if schedule_timesteps is None else schedule_timesteps
-        cand = (st == timestep).nonzero()
-        if len(cand) == 0:
+        """Position of `timestep` in the schedule with the reference's tie rule (dpmsolver.py:618-637): a value that
+        occurs twice resolves to its SECOND occurrence, an absent value to the last step."""
+        table = self.timesteps if schedule_timesteps is None else schedule_timesteps
+        hits = torch.nonzero(table == torch.as_tensor(timestep).to(table.device)).flatten().tolist()
+        if not hits:
             return len(self.timesteps) - 1
-        return cand[1].item() if len(cand) > 1 else cand[0].item()
+        return hits[min(1, len(hits) - 1)]
 
     def _init_step_index(self, timestep):
-        if self._begin_index is None:
-            if isinstance(timestep, torch.Tensor):
-                timestep = timestep.to(self.timesteps.device)
-            self._step_index = self.index_for_timestep(timestep)
-        else:
-            self._step_index = self._begin_index
+        self._step_index = self.index_for_timestep(timestep) if self._begin_index is None else self._begin_index
 
     def __len__(self):
         return self.config.num_train_timesteps
@@ -226,18 +223,3 @@ class EDMDPMSolverMultistepScheduler:
         if not return_dict:
             return (prev,)
         return SchedulerOutput(prev_sample=prev)
-
-    def add_noise(self, original_samples, noise, timesteps):
-        sigmas = self.sigmas.to(device=original_samples.device, dtype=original_samples.dtype)
-        st = self.timesteps.to(original_samples.device)
-        timesteps = timesteps.to(original_samples.device)
-        if self._begin_index is None:
-            idx = [self.index_for_timestep(t, st) for t in timesteps]
-        elif self._step_index is not None:
-            idx = [self._step_index] * timesteps.shape[0]
-        else:
-            idx = [self._begin_index] * timesteps.shape[0]
-        sigma = sigmas[idx].flatten()
-        while len(sigma.shape) < len(original_samples.shape):
-            sigma = sigma.unsqueeze(-1)
-        return original_samples + noise * sigma

@@ -173,6 +173,9 @@ def test_world_pipeline_drop_in_surface_from_pretrained_to_bind_get(tmp_path):
                           cond_snr=world.kwargs["cond_snr"], histogram_raw=world.kwargs["histogram_raw"],
                           latents_means=world.cond_input_mean, latents_stds=world.cond_input_std,
                           decoder_tile_size=128, decoder_tile_stride=96, residual_mean=0.1, residual_std=1.2)
+    ref_out = ref.get(-30, 10, 34, 106, with_climate=True)        # the same request sequence -> the same tile batches
+    assert ref_out["elev"].is_cuda and torch.equal(ref_out["elev"].cpu(), out["elev"])
+    assert torch.equal(ref_out["climate"].cpu(), out["climate"])
     assert torch.equal(ref.residual[:, -30:34, 10:106].cpu(), r)
     assert world.change_seed(12) is True and len(world._residual.done) == 0
     with pytest.raises(NotImplementedError):
