@@ -25,6 +25,10 @@ NVCC_FLAGS = [
 ]
 
 
+if os.environ.get("TDX_DEBUG_HOOKS") == "1":      # ablation flags / trace clocks / launch timeline for tools/trace_igemm.py etc.
+    NVCC_FLAGS.append("-DTDX_DEBUG_HOOKS=1")
+
+
 def _sources() -> list[Path]:
     return sorted(CSRC.glob("*.cu"))
 

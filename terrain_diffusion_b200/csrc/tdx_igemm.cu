@@ -117,10 +117,22 @@ __device__ __forceinline__ void stage_locate(const IgemmParams& p, int s, int& s
   tap = (s - base) - ch * taps;
 }
 
+// Debug hooks (ablation flags, per-item phase clocks, in-graph launch timeline: tools/trace_igemm.py,
+// tools/timeline_forward.py) are compiled in only with -DTDX_DEBUG_HOOKS=1 (TDX_DEBUG_HOOKS=1 python -m
+// terrain_diffusion_b200.build): in the production kernel they would cost ~40 instructions per item and epilogue warp.
+#ifndef TDX_DEBUG_HOOKS
+#define TDX_DEBUG_HOOKS 0
+#endif
+#if TDX_DEBUG_HOOKS
+#define TDX_DBG(bit) (p.dbg & (bit))
 #define TDX_TRACE(slot, it)                                                                  \
   do {                                                                                       \
     if (p.trace && blockIdx.x == 0 && (it) < 16) p.trace[(it) * 8 + (slot)] = clock64();     \
   } while (0)
+#else
+#define TDX_DBG(bit) 0
+#define TDX_TRACE(slot, it) do { } while (0)
+#endif
 
 // item = ((tile * nsplit) + split) * ksplit + kpart.  A CTA's items are blockIdx.x, blockIdx.x + gridDim.x, ...;
 // gridDim.x is a multiple of nsplit * ksplit, so the channel slice and the K part are fixed per CTA and only the M tile
@@ -283,12 +295,14 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CU
   // registers -- every UTCHMMA / TMA / mbarrier operand then costs an R2UR.
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
+#if TDX_DEBUG_HOOKS
   if (p.trace && blockIdx.x == 0 && threadIdx.x == 0) p.trace[126] = clock64();
   if (p.timeline && threadIdx.x == 0) {
     unsigned long long t;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
     atomicMin(p.timeline, t);
   }
+#endif
 
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&tm0);
@@ -322,7 +336,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CU
   tc_fence_after();
   if (p.cluster_stats) cluster_sync_all();   // peers' barriers are initialised before anyone arrives on them
   const uint32_t tmem_base = *tmem_slot;
+#if TDX_DEBUG_HOOKS
   if (p.trace && blockIdx.x == 0 && threadIdx.x == 0) p.trace[127] = clock64();
+#endif
   // Let the next kernel in the stream start its own prologue as soon as SMs free up (it still waits for our memory).
   pdl_launch_dependents();
 
@@ -377,7 +393,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CU
         for (int ks = 0; ks < st1 - st0; ++ks) {
           mbar_wait(&b_empty[sb], ph ^ 1, 200 + sb);
           if (elect_one()) {
-            if (p.dbg & 2) {
+            if (TDX_DBG(2)) {
               mbar_arrive(&b_full[sb]);
             } else {
               mbar_expect_tx(&b_full[sb], p.b_stage_bytes);
@@ -403,7 +419,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CU
           if (first) head = sb;
           if (elect_one()) {
             uint64_t* full = &b_full[head];
-            if (p.dbg & 2) {
+            if (TDX_DBG(2)) {
               if (first) mbar_arrive(full);
             } else {
               if (first) mbar_expect_tx(full, (uint32_t)(nt - t < p.bgroup ? nt - t : p.bgroup) * p.b_stage_bytes);
@@ -431,7 +447,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CU
     // updated with uniform arithmetic; descriptors are (constant upper word, low word = base + compile-time offset).
     const uint32_t idesc = uni(make_idesc_bf16(128, p.ncta));
     const uint32_t b_lbo = p.ncta * 16;
-    const uint32_t a_sbo = (p.dbg & 1) ? 128 : kPatchW * 16;
+    const uint32_t a_sbo = TDX_DBG(1) ? 128 : kPatchW * 16;
     const uint64_t a_hi = make_smem_desc(0, kKcBytes, a_sbo);
     const uint64_t b_hi = make_smem_desc(0, b_lbo, 128);
     const uint32_t a_h = uni((uint32_t)(a_hi >> 32)), b_h = uni((uint32_t)(b_hi >> 32));
@@ -521,7 +537,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CU
     if (p.ksplit > 1) cluster_sync_all();
   } else if (warp == 3) {
     if (p.ksplit > 1) cluster_sync_all();
-  } else if (warp >= 4 && !(p.dbg & 8)) {
+  } else if (warp >= 4 && !TDX_DBG(8)) {
     // ------------------------------------------------------------------ epilogue (TMEM -> registers -> global)
     // Warp w reads TMEM lane quadrant q = w & 3 (pixels q*32 .. q*32+31, one per lane); the kWQ warps of a quadrant
     // (wq = 0 .. kWQ-1) take the item's kChunk-column chunks round-robin.
@@ -638,7 +654,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CU
         const uint4* rbase = rbase_pre;
         if (has_resid && p.resid_inv) {
           rscale = p.resid_scale * rinv_pre;
-        } else if (has_resid && p.resid_pnorm && !(p.dbg & 32)) {
+        } else if (has_resid && p.resid_pnorm && !TDX_DBG(32)) {
           // the residual's pixel-norm runs over ALL Cout channels: the kWQ warps of a pixel quadrant each read their
           // share of the 8-channel planes (C8 is a multiple of 8) and combine through shared memory
           float ss = 0.f;
@@ -671,7 +687,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CU
 #pragma unroll
         for (int o = 0; o < 3; ++o) {
           const int sp = p.out[o].spatial;
-          oact[o] = (p.out[o].kind != TDX_OUT_NONE) && valid && !(sp == TDX_SP_DOWN2 && ((Y | X) & 1)) && !(p.dbg & 16);
+          oact[o] = (p.out[o].kind != TDX_OUT_NONE) && valid && !(sp == TDX_SP_DOWN2 && ((Y | X) & 1)) && !TDX_DBG(16);
           const uint32_t oplane = sp == TDX_SP_DOWN2 ? (plane >> 2) : (sp == TDX_SP_UP2 ? (plane << 2) : plane);
           optr[o] = reinterpret_cast<uint4*>(p.out[o].ptr) + pixel_off(sp) + (size_t)(chbase >> 3) * oplane;
         }
@@ -723,7 +739,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CU
 #pragma unroll
           for (int o = 0; o < 3; ++o) {
             const int kind = p.out[o].kind, sp = p.out[o].spatial;
-            if (kind == TDX_OUT_NONE || ((p.dbg & 64) && o > 0)) continue;
+            if (kind == TDX_OUT_NONE || (TDX_DBG(64) && o > 0)) continue;
             float hs = 0.5f * p.out[o].scale;
             if (kind == TDX_OUT_PNORM_SILU) hs = (p.epi & TDX_EPI_PNORM) ? 0.5f : 0.5f * inv;
             const uint32_t oplane = sp == TDX_SP_DOWN2 ? (plane >> 2) : (sp == TDX_SP_UP2 ? (plane << 2) : plane);
@@ -769,7 +785,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CU
           return inv_rms(tot, p.inv_cout);
         };
 
-        if (!(p.dbg & 4)) {
+        if (!TDX_DBG(4)) {
           // One code path for all cases (keeps the kernel small enough for the instruction cache): an optional
           // statistics pass, then the emitting pass.  When every warp has at most one chunk, it stays in registers
           // across the statistics exchange instead of being recomputed.
@@ -810,12 +826,14 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CU
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
+#if TDX_DEBUG_HOOKS
   if (p.trace && blockIdx.x == 0 && threadIdx.x == 96) p.trace[125] = clock64();
   if (p.timeline && threadIdx.x == 0) {
     unsigned long long t;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
     atomicMax(p.timeline + 1, t);
   }
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------------- host side

@@ -22,9 +22,26 @@ from .solve import DiffusionSolve
 from .tiling import linear_weight_window, tile_starts
 
 
+MAX_CACHED_SOLVES = 12      # every cached solve owns an activation arena and a CUDA graph
+
+
+class _LruDict(dict):
+    """dict that keeps at most MAX_CACHED_SOLVES entries, dropping the least recently inserted / fetched."""
+
+    def __getitem__(self, k):
+        v = super().pop(k)
+        super().__setitem__(k, v)
+        return v
+
+    def __setitem__(self, k, v):
+        super().__setitem__(k, v)
+        while len(self) > MAX_CACHED_SOLVES:
+            super().pop(next(iter(self)))
+
+
 def _solve_cache(model):
     if not hasattr(model, "_solve_cache"):
-        model._solve_cache = {}
+        model._solve_cache = _LruDict()
     return model._solve_cache
 
 

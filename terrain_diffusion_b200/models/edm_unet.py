@@ -142,6 +142,7 @@ class EDMUnet2D(nn.Module):
         self.logvar_linear = _Weight(n_logvar, logvar_channels)
         self._folded = None
         self._plans: dict = {}
+        self.max_cached_plans = 8
         self.use_cuda_graph = True
 
     # ------------------------------------------------------------------ diffusers-like surface
@@ -248,6 +249,10 @@ class EDMUnet2D(nn.Module):
             em.emit_embed(prog, labels=bufs.labels, emb_in=bufs.emb)
             em.emit(prog, [(bufs.x, fw.in_channels, None)], model_out=bufs.out)
             self._plans[key] = (prog, bufs)
+            while len(self._plans) > self.max_cached_plans:       # every plan owns a full activation arena + a graph
+                self._plans.pop(next(iter(self._plans)))
+        else:
+            self._plans[key] = self._plans.pop(key)               # most recently used last
         return self._plans[key]
 
     @torch.no_grad()

@@ -5,6 +5,12 @@ import os
 import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+# the hooks this tool reads are compiled out of the production kernel: (re)build libtdx.so with them
+# (run `python -m terrain_diffusion_b200.build` afterwards to get the production library back)
+os.environ["TDX_DEBUG_HOOKS"] = "1"
+from terrain_diffusion_b200.build import build as _build  # noqa: E402
+import importlib, terrain_diffusion_b200.build as _b  # noqa: E402
+importlib.reload(_b).build()
 import torch
 
 from oracle import unet as O
