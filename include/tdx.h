@@ -43,8 +43,7 @@ int tdx_abi_sizeof(int which);
  * ------------------------------------------------------------------------------------------------------------------ */
 enum { TDX_OUT_NONE = 0, TDX_OUT_RAW = 1, TDX_OUT_SILU = 2, TDX_OUT_PNORM_SILU = 3 };
 enum { TDX_SP_SAME = 0, TDX_SP_DOWN2 = 1, TDX_SP_UP2 = 2 };
-enum { TDX_EPI_EMB_SILU = 1, TDX_EPI_RESID = 2, TDX_EPI_PNORM = 4,
-       TDX_EPI_CVEC_HALF = 8 /* cvec holds c/2 (TdxEmbedDesc.cvec_scale = 0.5): saves a multiply per value */ };
+enum { TDX_EPI_EMB_SILU = 1, TDX_EPI_RESID = 2, TDX_EPI_PNORM = 4 };
 
 typedef struct TdxOutSpec {
   void* ptr;      /* bf16 NC8HW8, Cout channels; spatial size per `spatial` */
@@ -175,8 +174,6 @@ typedef struct TdxEmbedDesc {
   int32_t n_img;
   int32_t n_blocks;
   const TdxEmbedBlock* blocks; /* HOST array of n_blocks entries (copied by the call) */
-  float cvec_scale;            /* the vectors are stored multiplied by this (0 means 1); 0.5 with TDX_EPI_CVEC_HALF */
-  int32_t _pad;
 } TdxEmbedDesc;
 int tdx_embed_run(const TdxEmbedDesc* desc, void* stream);
 

@@ -60,7 +60,7 @@ class TdxEmbedDesc(C.Structure):
     _fields_ = [
         ("noise_labels", C.c_void_p), ("emb_in", C.c_void_p), ("noise_weight", C.c_void_p),
         ("noise_freqs", C.c_void_p), ("noise_dims", C.c_int32), ("emb_channels", C.c_int32), ("n_img", C.c_int32),
-        ("n_blocks", C.c_int32), ("blocks", C.POINTER(TdxEmbedBlock)), ("cvec_scale", C.c_float), ("_pad", C.c_int32),
+        ("n_blocks", C.c_int32), ("blocks", C.POINTER(TdxEmbedBlock)),
     ]
 
 
@@ -74,7 +74,7 @@ ABI_STRUCTS = [TdxOutSpec, TdxIgemmDesc, TdxConvInDesc, TdxConvOutDesc, TdxEmbed
 
 OUT_NONE, OUT_RAW, OUT_SILU, OUT_PNORM_SILU = 0, 1, 2, 3
 SP_SAME, SP_DOWN2, SP_UP2 = 0, 1, 2
-EPI_EMB_SILU, EPI_RESID, EPI_PNORM, EPI_CVEC_HALF = 1, 2, 4, 8
+EPI_EMB_SILU, EPI_RESID, EPI_PNORM = 1, 2, 4
 
 _lib = None
 

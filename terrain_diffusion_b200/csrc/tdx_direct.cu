@@ -469,7 +469,6 @@ struct EmbedParams {
   const float* noise_weight;
   const float* noise_freqs;
   int noise_dims, E;
-  float cvec_scale;
   TdxEmbedBlock blocks[kMaxEmbedBlocks];
 };
 
@@ -548,7 +547,7 @@ __global__ void __launch_bounds__(256) embed_kernel(const __grid_constant__ Embe
   float tot = 0.f;
 #pragma unroll
   for (int w = 0; w < 8; ++w) tot += red[w];
-  const float inv = rsqrtf(tot / (float)blk.c_out + 1e-8f) * p.cvec_scale;
+  const float inv = rsqrtf(tot / (float)blk.c_out + 1e-8f);
   for (int nn = threadIdx.x; nn < blk.c_out; nn += blockDim.x) blk.cvec[(size_t)img * blk.c_out + nn] = cfull[nn] * inv;
 }
 
@@ -580,7 +579,6 @@ int embed_launch(const TdxEmbedDesc& d, cudaStream_t stream) {
   p.noise_freqs = d.noise_freqs;
   p.noise_dims = d.noise_dims;
   p.E = d.emb_channels;
-  p.cvec_scale = d.cvec_scale == 0.f ? 1.f : d.cvec_scale;
   for (int b = 0; b < d.n_blocks; ++b) p.blocks[b] = d.blocks[b];
   dim3 grid(d.n_blocks, d.n_img);
   cudaLaunchConfig_t cfg;

@@ -123,9 +123,6 @@ __device__ __forceinline__ void stage_locate(const IgemmParams& p, int s, int& s
 #ifndef TDX_DEBUG_HOOKS
 #define TDX_DEBUG_HOOKS 0
 #endif
-#ifndef TDX_V_GUARD
-#define TDX_V_GUARD 1
-#endif
 #if TDX_DEBUG_HOOKS
 #define TDX_DBG(bit) (p.dbg & (bit))
 #define TDX_TRACE(slot, it)                                                                  \
@@ -689,16 +686,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CU
         bool oact[3];
 #pragma unroll
         for (int o = 0; o < 3; ++o) {
-#if TDX_V_GUARD
-          oact[o] = false;
-          optr[o] = nullptr;
-          if (p.out[o].kind == TDX_OUT_NONE) continue;          // (uniform: unused outputs cost one branch per item)
-          const int sp = p.out[o].spatial;
-          oact[o] = valid && !(sp == TDX_SP_DOWN2 && ((Y | X) & 1)) && !TDX_DBG(16);
-#else
           const int sp = p.out[o].spatial;
           oact[o] = (p.out[o].kind != TDX_OUT_NONE) && valid && !(sp == TDX_SP_DOWN2 && ((Y | X) & 1)) && !TDX_DBG(16);
-#endif
           const uint32_t oplane = sp == TDX_SP_DOWN2 ? (plane >> 2) : (sp == TDX_SP_UP2 ? (plane << 2) : plane);
           optr[o] = reinterpret_cast<uint4*>(p.out[o].ptr) + pixel_off(sp) + (size_t)(chbase >> 3) * oplane;
         }
@@ -714,25 +703,13 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CU
           load_acc(taddr_e + ck * kChunk, v);
           add_partials(ck, v);
           if (p.epi & TDX_EPI_EMB_SILU) {
-            if (p.epi & TDX_EPI_CVEC_HALF) {
-              // cvec holds c / 2: h = v * (c/2) is the tanh argument, mp_silu = (h / 0.596) * (1 + tanh h)
 #pragma unroll
-              for (int i = 0; i < kChunk; i += 4) {
-                const float4 c4 = __ldg(reinterpret_cast<const float4*>(cvb + ck * kChunk + i));
-                v[i + 0] = mp_silu_half(v[i + 0] * c4.x);
-                v[i + 1] = mp_silu_half(v[i + 1] * c4.y);
-                v[i + 2] = mp_silu_half(v[i + 2] * c4.z);
-                v[i + 3] = mp_silu_half(v[i + 3] * c4.w);
-              }
-            } else {
-#pragma unroll
-              for (int i = 0; i < kChunk; i += 4) {
-                const float4 c4 = __ldg(reinterpret_cast<const float4*>(cvb + ck * kChunk + i));
-                v[i + 0] = mp_silu_f(v[i + 0] * c4.x);
-                v[i + 1] = mp_silu_f(v[i + 1] * c4.y);
-                v[i + 2] = mp_silu_f(v[i + 2] * c4.z);
-                v[i + 3] = mp_silu_f(v[i + 3] * c4.w);
-              }
+            for (int i = 0; i < kChunk; i += 4) {
+              const float4 c4 = __ldg(reinterpret_cast<const float4*>(cvb + ck * kChunk + i));
+              v[i + 0] = mp_silu_f(v[i + 0] * c4.x);
+              v[i + 1] = mp_silu_f(v[i + 1] * c4.y);
+              v[i + 2] = mp_silu_f(v[i + 2] * c4.z);
+              v[i + 3] = mp_silu_f(v[i + 3] * c4.w);
             }
           }
           if (p.epi & TDX_EPI_RESID) {

@@ -53,53 +53,46 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 // Bounded wait: a broken pipeline traps (visible as a CUDA error on the host) instead of hanging the GPU box.  The
 // bound is a spin count (a try_wait suspends the thread for a hardware-defined time, ~1 us at most) and the report
 // lives in a function that is never inlined, so a wait site is five instructions in the instruction stream.
+// Bounded wait: a broken pipeline traps (visible as a CUDA error on the host) instead of hanging the GPU box.
+// TDX_V_WAIT selects how the time-out is raised (measured, profiles/r02_epilogue_diet_ab.txt):
+//   0  printf + trap inline in the wait loop
+//   1  a noinline, NORETURN reporter, loop bounded by the clock      2  the same, loop bounded by a poll counter
+// A plain noinline reporter (returning as far as the caller knows) costs 12 % of the whole step: a call that may
+// return clobbers the uniform registers, so the MMA issuer's ring state is spilled / re-converted (R2UR) around every
+// wait.  How often try_wait is re-polled (clock read between polls, suspend-time hint, nanosleep) makes no difference.
+#ifndef TDX_V_WAIT
+#define TDX_V_WAIT 1
+#endif
+#ifndef TDX_WAIT_LIMIT
+#define TDX_WAIT_LIMIT (1ll << 31)   // ~1 s of SM clocks
+#endif
 #ifndef TDX_WAIT_SPINS
 #define TDX_WAIT_SPINS (1u << 24)
 #endif
-static __device__ __noinline__ void mbar_timeout(int tag, uint32_t parity) {
+#if TDX_V_WAIT == 0
+__device__ __forceinline__ void mbar_timeout(int tag, uint32_t parity) {
   printf("tdx: mbarrier wait timeout tag=%d block=%d thread=%d parity=%u\n", tag, (int)blockIdx.x, (int)threadIdx.x,
          parity);
   __trap();
 }
-// Spin policy of a blocked wait (TDX_V_WAIT; measured on the 1x256^2 bench, profiles/r02_wait_policy.txt):
-//   0  re-poll after reading the clock (the ~30-cycle CS2R throttles the polling)      1  re-poll immediately
-//   2  re-poll immediately, try_wait carries a 20 us suspend-time hint                  3  clock + hint
-//   4  nanosleep(64) between polls
-// Re-polling immediately costs 12 % of the whole step: twelve warps hammering try_wait take issue slots and mbarrier
-// bandwidth from the MMA issuer and the TMA producers.
-#ifndef TDX_V_WAIT
-#define TDX_V_WAIT 0
-#endif
-__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity) {
-#if TDX_V_WAIT == 2 || TDX_V_WAIT == 3
-  uint32_t ok;
-  asm volatile(
-      "{\n\t"
-      ".reg .pred P;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
-      "selp.b32 %0, 1, 0, P;\n\t"
-      "}\n"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)
-      : "memory");
-  return ok != 0;
 #else
-  return mbar_try_wait(bar, parity);
-#endif
+static __device__ __noinline__ __attribute__((noreturn)) void mbar_timeout(int tag, uint32_t parity) {
+  printf("tdx: mbarrier wait timeout tag=%d block=%d thread=%d parity=%u\n", tag, (int)blockIdx.x, (int)threadIdx.x,
+         parity);
+  __trap();
+  for (;;) {}
 }
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag) {
   if (mbar_try_wait(bar, parity)) return;
-#if TDX_V_WAIT == 0 || TDX_V_WAIT == 3
+#if TDX_V_WAIT != 2
   long long t0 = clock64();
-  while (!mbar_try_wait_hint(bar, parity)) {
-    if (clock64() - t0 > (1ll << 31)) mbar_timeout(tag, parity);
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > TDX_WAIT_LIMIT) mbar_timeout(tag, parity);
   }
 #else
   uint32_t spins = 0;
-  while (!mbar_try_wait_hint(bar, parity)) {
-#if TDX_V_WAIT == 4
-    __nanosleep(64);
-#endif
+  while (!mbar_try_wait(bar, parity)) {
     if (++spins > TDX_WAIT_SPINS) mbar_timeout(tag, parity);
   }
 #endif
@@ -219,11 +212,6 @@ __device__ __forceinline__ float mp_silu_scaled(float x, float half_s, float hal
 }
 __device__ __forceinline__ float mp_silu_f(float x) {
   return mp_silu_scaled(x, 0.5f, 0.5f / 0.596f);
-}
-// the same with the argument already halved: h = z/2  ->  mp_silu(z) = (h / 0.596) * (1 + tanh h)
-__device__ __forceinline__ float mp_silu_half(float h) {
-  const float hk = h * (1.0f / 0.596f);
-  return fmaf(hk, tanh_approx(h), hk);
 }
 
 // Programmatic dependent launch (PDL): let the next kernel's prologue overlap this kernel's tail, and wait for the

@@ -29,7 +29,6 @@ from .. import _lib as L
 from ..layout import pack_weight_segments
 
 
-CVEC_HALF = os.environ.get("TDX_CVEC_HALF", "1") != "0"
 _TUNED = None
 _TUNED_NEW: dict = {}      # shapes measured in this process (TDX_AUTOTUNE=1); tools/tune_igemm.py writes them out
 _TUNE_CANDIDATES: dict = {}   # TDX_AUTOTUNE=2: valid (N, k_split) per shape key, in program order
@@ -535,7 +534,6 @@ class UNetEmitter:
             ed.noise_freqs = g["noise_freqs"].data_ptr()
             ed.noise_dims = fw.noise_dims
         ed.emb_channels = fw.emb_channels
-        ed.cvec_scale = 0.5 if CVEC_HALF else 1.0   # the igemm epilogues take c / 2 (TDX_EPI_CVEC_HALF)
         ed.n_img = rows
         ed.n_blocks = len(blocks)
         ed.blocks = arr
@@ -619,7 +617,7 @@ class UNetEmitter:
                         resid_pn = 0
                 hbuf = self.act(key + "h", cout, h, w)
                 d = self._igemm(prog, [(a_in, cout, 9)], key + "res0", cout, h, w)
-                d.epi_flags = L.EPI_EMB_SILU | (L.EPI_CVEC_HALF if CVEC_HALF else 0)
+                d.epi_flags = L.EPI_EMB_SILU
                 d.cvec = self._cvec_ptr(key, cout, cvec_set)
                 self._set_out(d, 0, hbuf, L.OUT_RAW)
                 self._add_igemm(prog, d)
@@ -646,7 +644,7 @@ class UNetEmitter:
                 else:
                     segs0 = [(cur["act"], b["cin"], 9)]
                 d = self._igemm(prog, segs0, key + "res0", cout, h, w)
-                d.epi_flags = L.EPI_EMB_SILU | (L.EPI_CVEC_HALF if CVEC_HALF else 0)
+                d.epi_flags = L.EPI_EMB_SILU
                 d.cvec = self._cvec_ptr(key, cout, cvec_set)
                 self._set_out(d, 0, hbuf, L.OUT_RAW)
                 self._add_igemm(prog, d)

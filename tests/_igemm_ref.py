@@ -100,7 +100,7 @@ def reference(case: Case, acts, wts, cvec, resid):
     return outs
 
 
-def run_cuda(case: Case, acts, wts, cvec, resid, cvec_half: bool = False):
+def run_cuda(case: Case, acts, wts, cvec, resid):
     dev = acts[0].device
     a_dev = [to_nc8hw8(a) for a in acts]
     n_item = case.n_item or L.igemm_choose_n(case.cout, case.n, case.h, case.w, case.segs)
@@ -116,8 +116,8 @@ def run_cuda(case: Case, acts, wts, cvec, resid, cvec_half: bool = False):
     d.c_out = case.cout
     d.n_per_item = n_item
     d.n_img, d.height, d.width = case.n, case.h, case.w
-    d.epi_flags = case.epi | (L.EPI_CVEC_HALF if cvec_half else 0)
-    cvec_dev = (cvec * 0.5 if cvec_half else cvec).contiguous()      # TDX_EPI_CVEC_HALF: the library is handed c / 2
+    d.epi_flags = case.epi
+    cvec_dev = cvec.contiguous()
     d.cvec = cvec_dev.data_ptr()
     d.resid = r_dev.data_ptr()
     d.resid_spatial = case.resid_spatial
