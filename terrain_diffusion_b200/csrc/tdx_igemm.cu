@@ -123,6 +123,15 @@ __device__ __forceinline__ void stage_locate(const IgemmParams& p, int s, int& s
 #ifndef TDX_DEBUG_HOOKS
 #define TDX_DEBUG_HOOKS 0
 #endif
+#ifndef TDX_V_TWO_KERNELS
+#define TDX_V_TWO_KERNELS 1
+#endif
+#ifndef TDX_V_AHEAD_R
+#define TDX_V_AHEAD_R 1
+#endif
+#ifndef TDX_V_AHEAD_C
+#define TDX_V_AHEAD_C 2
+#endif
 #if TDX_DEBUG_HOOKS
 #define TDX_DBG(bit) (p.dbg & (bit))
 #define TDX_TRACE(slot, it)                                                                  \
@@ -270,10 +279,15 @@ __device__ __forceinline__ void store_chunk(uint4* dst, uint32_t plane, int Wo, 
   }
 }
 
+// kCL = the launch uses clusters (split-K and / or pixel-norm statistics across CTAs).  The many-item launches do not:
+// their instantiation carries none of that code (a shorter epilogue loop, fewer instruction-cache misses).
+template <bool kCL>
 __global__ void __launch_bounds__(kThreads, 1)
 igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1,
              const __grid_constant__ CUtensorMap tm2, const __grid_constant__ IgemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
+  const int ksplit_ = kCL ? p.ksplit : 1;
+  const bool cstats_ = kCL && p.cluster_stats;
   uint8_t* a_ring = smem;
   uint8_t* b_ring = smem + kSA * kAStageBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(b_ring + p.SB * p.b_stage_bytes);
@@ -334,7 +348,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CU
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if (p.cluster_stats) cluster_sync_all();   // peers' barriers are initialised before anyone arrives on them
+  if (cstats_) cluster_sync_all();   // peers' barriers are initialised before anyone arrives on them
   const uint32_t tmem_base = *tmem_slot;
 #if TDX_DEBUG_HOOKS
   if (p.trace && blockIdx.x == 0 && threadIdx.x == 0) p.trace[127] = clock64();
@@ -369,7 +383,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CU
         s += taps - tap;   // the rest of this chunk's taps use the same patch
       }
     }
-    if (p.ksplit > 1) cluster_sync_all();   // split-K hand-over barrier (see the epilogue)
+    if (ksplit_ > 1) cluster_sync_all();   // split-K hand-over barrier (see the epilogue)
   } else if (warp == 1) {
     // ------------------------------------------------------------------ B producer (pre-packed weight stages)
     // Weights are constants: no dependency on the previous kernel, so this starts streaming during its tail.
@@ -435,7 +449,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CU
       }
       if (p.resident) break;   // the ring now holds this CTA's whole weight slice for every later item
     }
-    if (p.ksplit > 1) cluster_sync_all();
+    if (ksplit_ > 1) cluster_sync_all();
   } else if (warp == 2) {
     // ------------------------------------------------------------------ MMA issuer (one elected lane issues)
     // Everything a UTCHMMA reads (two 64-bit matrix descriptors, the TMEM address, the instruction descriptor) lives
@@ -534,9 +548,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CU
       __syncwarp();
       if (lane == 0) TDX_TRACE(3, it);
     }
-    if (p.ksplit > 1) cluster_sync_all();
+    if (ksplit_ > 1) cluster_sync_all();
   } else if (warp == 3) {
-    if (p.ksplit > 1) cluster_sync_all();
+    if (ksplit_ > 1) cluster_sync_all();
   } else if (warp >= 4 && !TDX_DBG(8)) {
     // ------------------------------------------------------------------ epilogue (TMEM -> registers -> global)
     // Warp w reads TMEM lane quadrant q = w & 3 (pixels q*32 .. q*32+31, one per lane); the kWQ warps of a quadrant
@@ -550,11 +564,11 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CU
     const bool need_norm = (p.epi & TDX_EPI_PNORM) || p.out[0].kind == TDX_OUT_PNORM_SILU ||
                            p.out[1].kind == TDX_OUT_PNORM_SILU || p.out[2].kind == TDX_OUT_PNORM_SILU ||
                            p.rms_out != nullptr;
-    const uint32_t my_rank = p.cluster_stats ? cluster_ctarank() : 0;
+    const uint32_t my_rank = cstats_ ? cluster_ctarank() : 0;
     TileWalk tw;
     tw.init(p);
     // Per-CTA constants: with split-K (one item per CTA) this part finalises `slice` of the item's columns.
-    const int ks = p.ksplit, kpart = tw.kpart;
+    const int ks = ksplit_, kpart = tw.kpart;
     const int slice = p.ncta / ks, sch = slice / kChunk;
     const int nchunks_all = p.ncta / kChunk;              // chunks of the whole accumulator tile
     const int nchunks = sch;                              // chunks this CTA finalises
@@ -570,17 +584,30 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CU
       return (uint32_t)(img_ * C8) * plane + (uint32_t)(Y_ * p.W + X_);
     };
     // Residual reads.  "UP2" = the residual is at half resolution, "DOWN2" = at double resolution (the inverse of an
-    // output's meaning).  Per item a thread needs its pixel's first-chunk channels (rpre) and, for the residual's
-    // pixel-norm, its share of ALL Cout channels (upre = the first four 8-channel planes of that share).
-    // (Requesting the NEXT item's values from inside the current item's epilogue was tried: the loads queue ahead of
-    // the output stores and the item gets slower, 28.4k -> 30.6k cycles on the 256^2 res1 layer.)
+    // output's meaning).
     const bool has_resid = (p.epi & TDX_EPI_RESID) != 0;
     const uint32_t rplane = p.resid_spatial == TDX_SP_UP2 ? (plane >> 2) : (p.resid_spatial == TDX_SP_DOWN2 ? (plane << 2) : plane);
     const int rsp = p.resid_spatial == TDX_SP_UP2 ? TDX_SP_DOWN2 : (p.resid_spatial == TDX_SP_DOWN2 ? TDX_SP_UP2 : TDX_SP_SAME);
-    uint4 upre[4], rpre[kGroups];
+    // The values an item needs from global memory before it can touch its accumulator are requested ONE ITEM AHEAD
+    // (`fetch_ahead`, called where the current item has consumed them): the residual's first-chunk channels or the
+    // modulation vector's first chunk (`pre`) and the residual's pixel-norm factor (`rinv_pre`).  Requested at the start of
+    // their own item, the factor alone cost 25-29 % of the epilogue of the residual layers (long-scoreboard stall on
+    // its first use, ncu source view, profiles/r02_epilogue_stalls.txt).
+    constexpr int kPreN = (kChunk / 4 > kGroups) ? kChunk / 4 : kGroups;
+    uint4 pre[kPreN];
     const uint4* rbase_pre = nullptr;
     float rinv_pre = 1.f;
-    auto resid_fetch = [&](const TileWalk& t) {
+    const bool cv_ahead = (TDX_V_AHEAD_C > 0) && (p.epi & TDX_EPI_EMB_SILU) && !has_resid;   // `pre` holds cvec (else: the residual)
+    const bool ahead = has_resid ? (TDX_V_AHEAD_R != 0) : (cv_ahead && TDX_V_AHEAD_C == 2);   // one item ahead / at the item's start
+    const bool own_rnorm = has_resid && p.resid_pnorm && !p.resid_inv;
+    auto fetch_ahead = [&](const TileWalk& t) {
+      if (cv_ahead) {
+        const uint4* cp = reinterpret_cast<const uint4*>(p.cvec + (size_t)t.img * p.cout + chbase + wq * kChunk);
+#pragma unroll
+        for (int j = 0; j < kChunk / 4; ++j) pre[j] = (wq < nchunks) ? __ldg(cp + j) : make_uint4(0, 0, 0, 0);
+        return;
+      }
+      if (!has_resid) return;
       const int Y_ = t.ty * kTileH + y, X_ = t.tx * kTileW + x;
       const bool vld = (Y_ < p.H) && (X_ < p.W);
       rbase_pre = p.resid + pixel_off_at(rsp, t.img, Y_, X_);
@@ -591,16 +618,12 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CU
                                               : (uint32_t)t.img * plane + (uint32_t)(Y_ * p.W + X_);
         rinv_pre = vld ? __ldg(p.resid_inv + po) : 0.f;
       }
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int g = wq * 2 + (j >> 1) * 2 * kWQ + (j & 1);
-        upre[j] = (vld && p.resid_pnorm && g < C8) ? __ldg(rbase_pre + (size_t)g * rplane) : make_uint4(0, 0, 0, 0);
-      }
       const uint4* rptr = rbase_pre + (size_t)((chbase >> 3) + wq * kGroups) * rplane;
 #pragma unroll
       for (int g = 0; g < kGroups; ++g)
-        rpre[g] = (vld && wq < nchunks) ? __ldg(rptr + (size_t)g * rplane) : make_uint4(0, 0, 0, 0);
+        pre[g] = (vld && wq < nchunks) ? __ldg(rptr + (size_t)g * rplane) : make_uint4(0, 0, 0, 0);
     };
+    if (ahead) fetch_ahead(tw);
     int it = 0;
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it, tw.next(p)) {
       const int acc = it & 1;
@@ -650,11 +673,14 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CU
       {
         // ---------------- general: residual mp_sum (+pixel-norm of the residual), clip, pixel-norm, up to 3 outputs
         float rscale = p.resid_scale;
-        if (has_resid) resid_fetch(tw);   // issued before the accumulator wait: overlaps the MMAs of this item
+        if (!ahead) fetch_ahead(tw);
         const uint4* rbase = rbase_pre;
+        const bool more = ahead && item + (int)gridDim.x < p.num_items;
+        TileWalk tn = tw;
+        tn.next(p);
         if (has_resid && p.resid_inv) {
           rscale = p.resid_scale * rinv_pre;
-        } else if (has_resid && p.resid_pnorm && !TDX_DBG(32)) {
+        } else if (own_rnorm && !TDX_DBG(32)) {
           // the residual's pixel-norm runs over ALL Cout channels: the kWQ warps of a pixel quadrant each read their
           // share of the 8-channel planes (C8 is a multiple of 8) and combine through shared memory
           float ss = 0.f;
@@ -665,10 +691,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CU
             unpack_bf16x2(u.z, a, b); ss = fmaf(a, a, fmaf(b, b, ss));
             unpack_bf16x2(u.w, a, b); ss = fmaf(a, a, fmaf(b, b, ss));
           };
-#pragma unroll
-          for (int j = 0; j < 4; ++j) sq8(upre[j]);
           if (valid) {
-            for (int g0 = wq * 2 + 4 * kWQ; g0 < C8; g0 += 2 * kWQ) {
+            for (int g0 = wq * 2; g0 < C8; g0 += 2 * kWQ) {
               const uint4 u0 = __ldg(rbase + (size_t)g0 * rplane), u1 = __ldg(rbase + (size_t)(g0 + 1) * rplane);
               sq8(u0);
               sq8(u1);
@@ -705,7 +729,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CU
           if (p.epi & TDX_EPI_EMB_SILU) {
 #pragma unroll
             for (int i = 0; i < kChunk; i += 4) {
-              const float4 c4 = __ldg(reinterpret_cast<const float4*>(cvb + ck * kChunk + i));
+              const uint4 cu = (cv_ahead && ck == wq) ? pre[i >> 2] : __ldg(reinterpret_cast<const uint4*>(cvb + ck * kChunk + i));
+              const float4 c4 = make_float4(__uint_as_float(cu.x), __uint_as_float(cu.y), __uint_as_float(cu.z), __uint_as_float(cu.w));
               v[i + 0] = mp_silu_f(v[i + 0] * c4.x);
               v[i + 1] = mp_silu_f(v[i + 1] * c4.y);
               v[i + 2] = mp_silu_f(v[i + 2] * c4.z);
@@ -716,7 +741,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CU
             const uint4* rptr = rbase + (size_t)((chbase >> 3) + ck * kGroups) * rplane;
 #pragma unroll
             for (int g = 0; g < kGroups; ++g) {
-              uint4 u = (ck == wq) ? rpre[g] : (valid ? __ldg(rptr + (size_t)g * rplane) : make_uint4(0, 0, 0, 0));
+              uint4 u = (ck == wq) ? pre[g] : (valid ? __ldg(rptr + (size_t)g * rplane) : make_uint4(0, 0, 0, 0));
               float rr[8];
               unpack_bf16x2(u.x, rr[0], rr[1]);
               unpack_bf16x2(u.y, rr[2], rr[3]);
@@ -756,7 +781,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CU
           float tot = 0.f;
 #pragma unroll
           for (int w = 0; w < kWQ; ++w) tot += ssq[w * 128 + m];
-          if (p.cluster_stats) {
+          if (cstats_) {
             // (2) combine the CTAs that hold the other channels of this M tile through distributed shared memory
             const int par = it & 1;
             if (wq == 0) {
@@ -793,7 +818,11 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CU
           for (int pass = need_norm ? 0 : 1; pass < 2; ++pass) {
 #pragma unroll 1
             for (int ck = wq; ck < nchunks; ck += kWQ) {
-              if (pass == 0 || !reuse) compute_v(ck, v);
+              if (pass == 0 || !reuse) {
+                compute_v(ck, v);
+                // `pre` (chunk wq of this item) has just been used for the last time: request the next item's
+                if (ck == wq && (reuse || pass == 1) && more) fetch_ahead(tn);
+              }
               if (pass == 0) {
 #pragma unroll
                 for (int i = 0; i < kChunk; ++i) sumsq = fmaf(v[i], v[i], sumsq);
@@ -818,7 +847,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CU
 
   tc_fence_before();
   __syncthreads();
-  if (p.cluster_stats) cluster_sync_all();   // nobody leaves while a peer may still write into its shared memory
+  if (cstats_) cluster_sync_all();   // nobody leaves while a peer may still write into its shared memory
   if (warp == 3) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
@@ -844,7 +873,8 @@ static int ensure_scratch(float** ws);
 int igemm_prepare() {
   static bool attr_set = false;
   if (!attr_set) {
-    TDX_CHECK_CUDA(cudaFuncSetAttribute(igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+    TDX_CHECK_CUDA(cudaFuncSetAttribute(igemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+    TDX_CHECK_CUDA(cudaFuncSetAttribute(igemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
     attr_set = true;
   }
   float* ws;
@@ -891,8 +921,8 @@ static int max_active_clusters(int csize) {
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   int n = 0;
-  cudaFuncSetAttribute(igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
-  if (cudaOccupancyMaxActiveClusters(&n, igemm_kernel, &cfg) != cudaSuccess || n <= 0) {
+  cudaFuncSetAttribute(igemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+  if (cudaOccupancyMaxActiveClusters(&n, igemm_kernel<true>, &cfg) != cudaSuccess || n <= 0) {
     cudaGetLastError();
     n = (sm_count() * 3 / 4) / csize;   // no GPU to ask (or the query failed): assume some GPCs cannot be filled
   }
@@ -1057,7 +1087,8 @@ int igemm_launch(const TdxIgemmDesc& d, const CUtensorMap* tms, cudaStream_t str
     cfg.attrs = attr;
     cfg.numAttrs += 1;
   }
-  TDX_CHECK_CUDA(cudaLaunchKernelEx(&cfg, igemm_kernel, t0, t1, t2, p));
+  if (cluster > 1 || !TDX_V_TWO_KERNELS) TDX_CHECK_CUDA(cudaLaunchKernelEx(&cfg, igemm_kernel<true>, t0, t1, t2, p));
+  else TDX_CHECK_CUDA(cudaLaunchKernelEx(&cfg, igemm_kernel<false>, t0, t1, t2, p));
   return TDX_OK;
 }
 
