@@ -870,46 +870,7 @@ static int g_dbg_flags = 0;
 
 static int ensure_scratch(float** ws);
 
-// Persisting-L2 carve-out for weights, per device (TDX_L2_PERSIST_MB, 0 = off; also off when the device has none).
-static size_t g_l2_persist[16] = {0};
-static size_t g_l2_window[16] = {0};
-static bool g_l2_asked[16] = {false};
-static void l2_setup() {
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16 || g_l2_asked[dev]) return;
-  g_l2_asked[dev] = true;
-  const char* e = getenv("TDX_L2_PERSIST_MB");
-  const long mb = e ? atol(e) : 48;
-  if (mb <= 0) return;
-  int max_persist = 0, max_window = 0;
-  if (cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev) != cudaSuccess ||
-      cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev) != cudaSuccess || max_persist <= 0 ||
-      max_window <= 0) {
-    cudaGetLastError();
-    return;
-  }
-  size_t want = (size_t)mb << 20;
-  if (want > (size_t)max_persist) want = (size_t)max_persist;
-  if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) != cudaSuccess) {
-    cudaGetLastError();
-    return;
-  }
-  g_l2_persist[dev] = want;
-  g_l2_window[dev] = (size_t)max_window;
-}
-static size_t l2_persist_bytes() {
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return 0;
-  return g_l2_persist[dev];
-}
-static size_t l2_window_max() {
-  int dev = 0;
-  cudaGetDevice(&dev);
-  return g_l2_window[dev];
-}
-
 int igemm_prepare() {
-  l2_setup();
   static bool attr_set = false;
   if (!attr_set) {
     TDX_CHECK_CUDA(cudaFuncSetAttribute(igemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
@@ -1116,23 +1077,8 @@ int igemm_launch(const TdxIgemmDesc& d, const CUtensorMap* tms, cudaStream_t str
   const CUtensorMap& t1 = tms[d.n_seg > 1 ? 1 : 0];
   const CUtensorMap& t2 = tms[d.n_seg > 2 ? 2 : 0];
   cudaLaunchConfig_t cfg;
-  cudaLaunchAttribute attr[3];
+  cudaLaunchAttribute attr[2];
   fill_launch_config(&cfg, attr, dim3(grid), dim3(kThreads), smem < 120 * 1024 ? 120 * 1024 : smem, stream);
-  // Weights of the layers whose traffic they dominate stay in the persisting part of L2 (igemm_prepare sets it aside):
-  // every step streams ~0.5 GB of activations through L2, which would otherwise evict the 56 MB the next step re-reads.
-  const size_t w_bytes = (size_t)p.stages_per_item * p.cout * 128;
-  const size_t act_bytes = (size_t)p.nimg * p.H * p.W * p.cout * 2;
-  if (l2_persist_bytes() > 0 && w_bytes >= act_bytes / 4) {
-    cudaLaunchAttribute& a = attr[cfg.numAttrs];
-    a.id = cudaLaunchAttributeAccessPolicyWindow;
-    a.val.accessPolicyWindow.base_ptr = const_cast<void*>(d.b_packed);
-    a.val.accessPolicyWindow.num_bytes = w_bytes < l2_window_max() ? w_bytes : l2_window_max();
-    a.val.accessPolicyWindow.hitRatio = 1.0f;
-    a.val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-    a.val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-    cfg.attrs = attr;
-    cfg.numAttrs += 1;
-  }
   if (cluster > 1) {
     attr[cfg.numAttrs].id = cudaLaunchAttributeClusterDimension;
     attr[cfg.numAttrs].val.clusterDim.x = cluster;
