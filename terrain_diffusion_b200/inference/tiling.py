@@ -9,6 +9,8 @@
 """
 from __future__ import annotations
 
+import functools
+
 import torch
 
 
@@ -32,14 +34,21 @@ def window_origin(k: int, stride: int, offset: int = 0) -> int:
     return k * stride + offset
 
 
-def linear_weight_window(size: int, device="cpu", dtype=torch.float32) -> torch.Tensor:
-    """[size, size] blend weights; computed on the host in the reference's op order (fp32-identical), then moved."""
+@functools.lru_cache(maxsize=32)
+def _linear_weight_window_cached(size: int, device: str, dtype) -> torch.Tensor:
     mid = (size - 1) / 2
     y, x = torch.meshgrid(torch.arange(size), torch.arange(size), indexing="ij")
     eps = 1e-3
     wy = 1 - (1 - eps) * torch.clamp(torch.abs(y - mid).to(dtype) / mid, 0, 1)
     wx = 1 - (1 - eps) * torch.clamp(torch.abs(x - mid).to(dtype) / mid, 0, 1)
     return (wy * wx).to(device)
+
+
+def linear_weight_window(size: int, device="cpu", dtype=torch.float32) -> torch.Tensor:
+    """[size, size] blend weights; computed on the host in the reference's op order (fp32-identical), then moved.
+    Cached per (size, device, dtype): every sampler call asks for the same window (the 256^2 host evaluation plus a
+    pageable copy was ~0.3 ms of each end-to-end solve).  Treat the result as read-only."""
+    return _linear_weight_window_cached(int(size), str(torch.device(device)), dtype)
 
 
 def padded_batch_size(n: int, max_batch: int) -> int:
