@@ -349,6 +349,128 @@ def run_canvas_arm(args, rank, local_rank, world):
     dist.destroy_process_group()
 
 
+# ----------------------------------------------------------------------------------------------------- latent arm
+BASE_CFG = dict(image_size=512, in_channels=5, out_channels=5, model_channels=192, model_channel_mults=[1, 2, 3, 4],
+                layers_per_block=3, attn_resolutions=[8, 16], midblock_attention=True, concat_balance=0.5,
+                conditional_inputs=[["tensor", 58, 1.0]], fourier_scale="pos", block_kwargs={"dropout": 0.1})
+"""configs/diffusion_base/diffusion_192-3.cfg:54-69 (253.7 M parameters; self-attention at 8^2 / 16^2)."""
+GFLOP_PER_LATENT_PHASE = 193.65   # one base-model forward on a 64^2 latent tile (SURVEY.md 8(d))
+
+
+def run_latent_arm(args, rank, local_rank, world):
+    """the latent consistency stage (world_pipeline.py:1052-1131) -- one TrigFlow phase of the 253 M
+    base U-Net (58-dim conditioning vector, self-attention) on batches of 64^2 latent tiles.  A step = one phase of one
+    tile; `value` with the batch resident, `e2e` through `latent_stage_tiles` (host coarse windows in, packed tiles back
+    to the host, tile noise generated on the device), which is what the pipeline's stage callback runs."""
+    import math
+    import torch.distributed as dist
+    from terrain_diffusion_b200.inference.samplers import get_consistency_solve
+    from terrain_diffusion_b200.inference.stages import latent_stage_tiles
+    from terrain_diffusion_b200.inference.tiling import linear_weight_window
+    from terrain_diffusion_b200.models import EDMUnet2D
+    from oracle import unet as ounet
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    model = EDMUnet2D(**BASE_CFG).eval()
+    model.load_state_dict(ounet.procedural_state_dict(BASE_CFG, seed=0))
+    model = model.to(dev)
+    B = args.tiles if args.tiles > 1 else 16                       # the product batches 16 windows (latents_batch_size)
+    T, sd = 64, 0.5
+    t_init = math.atan(80.0 / sd)
+    g = torch.Generator().manual_seed(3 + rank)
+    z = torch.randn(B, 5, T, T, generator=g).to(dev)
+    cvec = torch.randn(B, 58, generator=g).to(dev)
+    solve = get_consistency_solve(model, B, T, T, t_init, sd, from_unit_noise=True, out_scale=1.0 / sd)
+    solve.prog.instantiate()
+    for _ in range(max(3, args.warmup)):
+        solve.run(z, None, conditional_inputs=[cvec])
+    torch.cuda.synchronize()
+    flush = torch.empty(192 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    flush.zero_()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    with ClockSampler(local_rank) as clk:
+        e0.record()
+        for _ in range(args.steps):
+            solve.run(z, None, conditional_inputs=[cvec])
+        e1.record()
+        torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t_ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms = float(t_ms.item())
+    value = world * B * args.steps / (ms / 1e3)
+    # e2e: the stage callback with host inputs / host outputs
+    ww = linear_weight_window(T, dev)
+    ctxs = [(0, i // 4, i % 4) for i in range(B)]
+    coarse_h = [torch.cat([torch.randn(6, 4, 4, generator=g), torch.ones(1, 4, 4)]).pin_memory() for _ in range(B)]
+    hist = torch.zeros(1, 5)
+    means, stds = torch.zeros(7), torch.ones(7)
+    out_h = torch.empty(B, 6, T, T).pin_memory()
+
+    def stage():
+        tiles = latent_stage_tiles(model, 1234, ctxs, None, coarse_h, t_init, ww, hist, means, stds, pad_batch_to=16)
+        out_h.copy_(torch.stack(tiles), non_blocking=True)
+        torch.cuda.synchronize()
+    e2e_value, e2e_err = None, None
+    try:
+        stage()
+        n_e = 5
+        t0 = time.perf_counter()
+        for _ in range(n_e):
+            stage()
+        e2e_value = world * B * n_e / (time.perf_counter() - t0)
+    except Exception as exc:                                       # the kernel-only number stands on its own
+        e2e_err = repr(exc)
+    roof = None
+    if rank == 0:
+        solve.run(z, None, conditional_inputs=[cvec])
+        solve.prog.profile()
+        msl, kinds = solve.prog.profile()
+        ig_ms = sum(m for m, k in zip(msl, kinds) if k == 1)
+        n_ig = sum(1 for k in kinds if k == 1)
+        share = ig_ms / sum(msl)
+        step_ms = ms / args.steps
+        flops = GFLOP_PER_LATENT_PHASE * 1e9 * B
+        achieved = flops / (step_ms * share / 1e3) / 1e12
+        peak = 1400.0
+        try:
+            peak = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()).get("bf16_tflops_sustained") or peak
+        except Exception:
+            pass
+        roof = {"bound": "tensor", "kernel": "tdx::igemm_kernel (tcgen05 implicit-GEMM conv)", "achieved": achieved,
+                "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None, "launches": n_ig,
+                "kernel_share_of_step": share, "avg_launch_us": step_ms * share / n_ig * 1e3,
+                "method": "as the default arm: per-launch CUDA events give the share, x graph-replayed step time"}
+        line = {"metric": "latent-stage tile-phases/sec, 64^2 latent tiles, base 253M U-Net", "value": value,
+                "unit": "tile-phases/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": f"SURVEY 8(f)-1: base U-Net (253.7M params, self-attention, 58-dim conditioning), "
+                                       f"{B} x 64x64 latent tiles per launch, one TrigFlow consistency phase per step",
+                           "tiles_per_gpu": B, "tile": T, "parallelism": f"tiles x{world}",
+                           "l2": "L2 flushed before the timed region; 507 MB of bf16 weights + the activation arena "
+                                 "stream through L2 every phase",
+                           "gflop_per_tile_phase": GFLOP_PER_LATENT_PHASE},
+                "clocks": clk.summary(),
+                "e2e": {"value": e2e_value, "unit": "tile-phases/s", "h2d_bytes_per_step": 7 * 16 * 4,
+                        "d2h_bytes_per_step": 6 * T * T * 4, "error": e2e_err,
+                        "api": "terrain_diffusion_b200.inference.stages.latent_stage_tiles"},
+                "gpu_launches": solve.launches_per_solve * args.steps, "roofline": roof,
+                "tflops": value * GFLOP_PER_LATENT_PHASE / 1e3}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 # ----------------------------------------------------------------------------------------------------- our arm
 def main():
     ap = argparse.ArgumentParser()
@@ -359,7 +481,7 @@ def main():
     ap.add_argument("--tiles", type=int, default=1, help="independent tiles solved together per GPU")
     ap.add_argument("--size", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="tiles", choices=["tiles", "canvas", "export"],
+    ap.add_argument("--workload", default="tiles", choices=["tiles", "canvas", "export", "latent"],
                     help="tiles (default, the BASELINE metric: independent 256^2 tiles per GPU, weak scaling) | canvas "
                          "(configs[2]: one 1664^2 canvas, strong scaling) | export (configs[3]-shaped 9344^2 canvas)")
     ap.add_argument("--solve-steps", type=int, default=SOLVE_STEPS, help="denoising steps per tile (canvas workloads)")
@@ -377,6 +499,9 @@ def main():
         return
     if args.impl == "reference-gpu":
         run_reference_gpu_arm(args, rank)
+        return
+    if args.workload == "latent":
+        run_latent_arm(args, rank, local_rank, world)
         return
     if args.workload != "tiles":
         run_canvas_arm(args, rank, local_rank, world)

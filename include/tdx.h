@@ -272,6 +272,12 @@ int tdx_noise_patch(uint64_t base_seed, int64_t y0, int64_t x0, int32_t h, int32
                     int32_t tile_h, int32_t tile_w, float* out, void* workspace, int64_t workspace_bytes,
                     void* stream);
 int64_t tdx_noise_patch_workspace_bytes(int32_t channels, int32_t tile_h, int32_t tile_w);
+/* Batched form (one call for all windows of a stage batch, world_pipeline.py:1085-1092 runs this per tile in a Python
+ * loop): n_patches patches of one shape, origins in HOST arrays, out = [n][C][h][w]; bit-identical to n single calls. */
+int tdx_noise_patches(uint64_t base_seed, int32_t n_patches, const int64_t* y0s, const int64_t* x0s, int32_t h, int32_t w,
+                      int32_t channels, int32_t tile_h, int32_t tile_w, float* out, void* workspace,
+                      int64_t workspace_bytes, void* stream);
+int64_t tdx_noise_patches_workspace_bytes(int32_t channels, int32_t tile_h, int32_t tile_w);
 /* portable_rng.standard_normal(seed, n) (inference/portable_rng.py:77-82): one raw stream, bit-exact;
  * workspace >= tdx_noise_patch_workspace_bytes(1, 1, n). */
 int tdx_standard_normal(uint64_t seed, int64_t n, float* out, void* workspace, int64_t workspace_bytes, void* stream);

@@ -158,6 +158,12 @@ def _declare(l: C.CDLL) -> None:
                                   C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
     l.tdx_noise_patch_workspace_bytes.restype = C.c_int64
     l.tdx_noise_patch_workspace_bytes.argtypes = [C.c_int32, C.c_int32, C.c_int32]
+    l.tdx_noise_patches.restype = C.c_int
+    l.tdx_noise_patches.argtypes = [C.c_uint64, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_int32,
+                                    C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64,
+                                    C.c_void_p]
+    l.tdx_noise_patches_workspace_bytes.restype = C.c_int64
+    l.tdx_noise_patches_workspace_bytes.argtypes = [C.c_int32, C.c_int32, C.c_int32]
     l.tdx_standard_normal.restype = C.c_int
     l.tdx_standard_normal.argtypes = [C.c_uint64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
     l.tdx_noise_patch_status.restype = C.c_int

@@ -145,6 +145,90 @@ __global__ void noise_emit_kernel(const NoiseEmit p, const int* offsets, long lo
   if (chunk == n_chunks - 1 && pos < p.n_out) *p.status = 1;
 }
 
+// ---- batched form: up to kBatchJobs (patch, tile) jobs per launch, job = blockIdx.y, one counts slice per job
+constexpr int kBatchJobs = 32;
+struct NoiseBatch {
+  int n_jobs;
+  long long n_chunks;
+  NoiseEmit job[kBatchJobs];
+};
+
+__global__ void noise_count_batch_kernel(const __grid_constant__ NoiseBatch b, int* counts) {
+  const NoiseEmit& p = b.job[blockIdx.y];
+  const long long chunk = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long p0 = chunk * kChunk;
+  if (p0 >= p.n_pairs) return;
+  unsigned long long state = lcg_jump(p.seed, 2ULL * (unsigned long long)p0);
+  int c = 0;
+  for (int i = 0; i < kChunk && p0 + i < p.n_pairs; ++i) {
+    double v1, v2, s;
+    c += polar_pair(state, v1, v2, s) ? 1 : 0;
+  }
+  counts[(long long)blockIdx.y * b.n_chunks + chunk] = c;
+}
+
+__device__ __forceinline__ void scan_block(int* counts, long long n) {
+  __shared__ int warp_tot[32];
+  __shared__ int carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (long long base = 0; base < n; base += blockDim.x) {
+    const long long i = base + threadIdx.x;
+    const int v = i < n ? counts[i] : 0;
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffff, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      int w = lane < (int)(blockDim.x >> 5) ? warp_tot[lane] : 0;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffff, w, o);
+        if (lane >= o) w += t;
+      }
+      warp_tot[lane] = w;
+    }
+    __syncthreads();
+    const int warp_off = warp == 0 ? 0 : warp_tot[warp - 1];
+    const int block_total = warp_tot[(blockDim.x >> 5) - 1];
+    if (i < n) counts[i] = carry + warp_off + incl - v;
+    __syncthreads();
+    if (threadIdx.x == 0) carry += block_total;
+    __syncthreads();
+  }
+}
+
+__global__ void noise_scan_batch_kernel(int* counts, long long n_chunks) {
+  scan_block(counts + (long long)blockIdx.x * n_chunks, n_chunks);
+}
+
+__global__ void noise_emit_batch_kernel(const __grid_constant__ NoiseBatch b, const int* counts) {
+  const NoiseEmit& p = b.job[blockIdx.y];
+  const int* offsets = counts + (long long)blockIdx.y * b.n_chunks;
+  const long long chunk = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (chunk >= b.n_chunks) return;
+  const long long p0 = chunk * kChunk;
+  long long pos = 2LL * offsets[chunk];
+  if (pos >= p.n_out) return;
+  unsigned long long state = lcg_jump(p.seed, 2ULL * (unsigned long long)p0);
+  for (int i = 0; i < kChunk && p0 + i < p.n_pairs; ++i) {
+    double v1, v2, s;
+    if (polar_pair(state, v1, v2, s)) {
+      const double f = sqrt(__ddiv_rn(__dmul_rn(-2.0, log(s)), s));
+      noise_store(p, pos, __dmul_rn(v1, f));
+      noise_store(p, pos + 1, __dmul_rn(v2, f));
+      pos += 2;
+      if (pos >= p.n_out) return;
+    }
+  }
+  if (chunk == b.n_chunks - 1 && pos < p.n_out) *p.status = 1;
+}
+
 static long long floordiv(long long a, long long b) {
   long long q = a / b;
   if ((a % b != 0) && ((a < 0) != (b < 0))) --q;
@@ -219,6 +303,76 @@ extern "C" int tdx_noise_patch(uint64_t base_seed, int64_t y0, int64_t x0, int32
   }
   TDX_CHECK_CUDA(cudaGetLastError());
   return TDX_OK;
+}
+
+/* Batched tdx_noise_patch: n_patches patches of one shape, origins in HOST arrays y0s / x0s, out = [n][C][h][w].
+ * Every (patch, covering tile) pair is one job; 32 jobs share a launch (three launches per 32 jobs instead of three per
+ * job).  workspace >= tdx_noise_patches_workspace_bytes(channels, tile_h, tile_w).  Bit-identical to the single form. */
+extern "C" int64_t tdx_noise_patches_workspace_bytes(int32_t channels, int32_t tile_h, int32_t tile_w) {
+  const long long n_out = (long long)channels * tile_h * tile_w;
+  const long long chunks = (pair_budget(n_out) + kChunk - 1) / kChunk;
+  return (int64_t)(chunks * sizeof(int) * kBatchJobs + 256);
+}
+
+extern "C" int tdx_noise_patches(uint64_t base_seed, int32_t n_patches, const int64_t* y0s, const int64_t* x0s, int32_t h,
+                                 int32_t w, int32_t channels, int32_t tile_h, int32_t tile_w, float* out,
+                                 void* workspace, int64_t workspace_bytes, void* stream_) {
+  TDX_REQUIRE(out && workspace && y0s && x0s, "noise_patches: null pointer");
+  TDX_REQUIRE(n_patches >= 1 && h >= 1 && w >= 1 && channels >= 1 && tile_h >= 1 && tile_w >= 1,
+              "noise_patches: bad shape");
+  TDX_REQUIRE(workspace_bytes >= tdx_noise_patches_workspace_bytes(channels, tile_h, tile_w),
+              "noise_patches: workspace too small (%lld bytes)", (long long)workspace_bytes);
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  const long long n_out = (long long)channels * tile_h * tile_w;
+  TDX_REQUIRE(n_out < (1LL << 30), "noise_patches: tile stream too long");
+  const long long n_pairs = pair_budget(n_out);
+  const long long n_chunks = (n_pairs + kChunk - 1) / kChunk;
+  int* status = reinterpret_cast<int*>(workspace);
+  int* counts = status + 64;
+  TDX_CHECK_CUDA(cudaMemsetAsync(status, 0, sizeof(int), stream));
+  const int threads = 128;
+  const int blocks = (int)((n_chunks + threads - 1) / threads);
+  NoiseBatch b;
+  b.n_jobs = 0;
+  b.n_chunks = n_chunks;
+  auto flush = [&]() -> int {
+    if (b.n_jobs == 0) return TDX_OK;
+    noise_count_batch_kernel<<<dim3(blocks, b.n_jobs), threads, 0, stream>>>(b, counts);
+    noise_scan_batch_kernel<<<b.n_jobs, 1024, 0, stream>>>(counts, n_chunks);
+    noise_emit_batch_kernel<<<dim3(blocks, b.n_jobs), threads, 0, stream>>>(b, counts);
+    TDX_CHECK_CUDA(cudaGetLastError());
+    b.n_jobs = 0;
+    return TDX_OK;
+  };
+  for (int i = 0; i < n_patches; ++i) {
+    const long long y0 = y0s[i], x0 = x0s[i];
+    const long long ty0 = floordiv(y0, tile_h), ty1 = floordiv(y0 + h - 1, tile_h);
+    const long long tx0 = floordiv(x0, tile_w), tx1 = floordiv(x0 + w - 1, tile_w);
+    for (long long ty = ty0; ty <= ty1; ++ty) {
+      for (long long tx = tx0; tx <= tx1; ++tx) {
+        NoiseEmit& p = b.job[b.n_jobs++];
+        p.seed = tile_seed(base_seed, ty, tx);
+        p.n_pairs = n_pairs;
+        p.n_out = n_out;
+        p.tile_h = tile_h;
+        p.tile_w = tile_w;
+        p.tile_y0 = ty * tile_h;
+        p.tile_x0 = tx * tile_w;
+        p.y0 = y0;
+        p.x0 = x0;
+        p.h = h;
+        p.w = w;
+        p.channels = channels;
+        p.out = out + (long long)i * channels * h * w;
+        p.status = status;
+        if (b.n_jobs == kBatchJobs) {
+          int rc = flush();
+          if (rc != TDX_OK) return rc;
+        }
+      }
+    }
+  }
+  return flush();
 }
 
 /* portable_rng.standard_normal(seed, n): ONE stream of n fp32 normals seeded directly with `seed` (no tile hash);

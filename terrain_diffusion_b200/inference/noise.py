@@ -56,6 +56,30 @@ def gaussian_noise_patch(base_seed: int, y0: int, x0: int, h: int, w: int, chann
     return out
 
 
+def gaussian_noise_patches(base_seed: int, origins, h: int, w: int, channels: int = 1, tile_h: int = 256,
+                           tile_w: int = 256, device="cuda") -> torch.Tensor:
+    """[n, C, h, w]: the patches at the integer world origins `origins` = [(y0, x0), ...] in ONE library call (three
+    launches per 32 (patch, tile) pairs); bit-identical to stacking gaussian_noise_patch results."""
+    import ctypes as C
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        raise L.TdxError("gaussian_noise_patches (B200 path) generates on the GPU; there is no CPU path")
+    n = len(origins)
+    out = torch.empty((n, channels, h, w), dtype=torch.float32, device=dev)
+    if n == 0:
+        return out
+    nbytes = int(L.lib().tdx_noise_patches_workspace_bytes(channels, tile_h, tile_w))
+    key = (dev, nbytes, L.current_stream_ptr(dev))
+    if key not in _workspaces:
+        _workspaces[key] = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    ws = _workspaces[key]
+    ys = (C.c_int64 * n)(*[int(o[0]) for o in origins])
+    xs = (C.c_int64 * n)(*[int(o[1]) for o in origins])
+    L.call(L.lib().tdx_noise_patches, dev, int(base_seed) & MASK64, n, ys, xs, h, w, channels, tile_h, tile_w,
+           out.data_ptr(), ws.data_ptr(), nbytes)
+    return out
+
+
 def standard_normal(seed: int, n: int, device="cuda") -> torch.Tensor:
     """portable_rng.standard_normal(seed, n) as an fp32 CUDA tensor (bit-identical stream)."""
     dev = torch.device(device)

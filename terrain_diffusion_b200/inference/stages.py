@@ -25,7 +25,7 @@ import math
 import torch
 
 from .. import _lib as L
-from .noise import gaussian_noise_patch
+from .noise import gaussian_noise_patch, gaussian_noise_patches
 from .samplers import get_consistency_solve, get_diffusion_solve
 from .tiling import padded_batch_size
 
@@ -125,11 +125,15 @@ def latent_stage_tiles(model, seed: int, ctxs, samples, cond_imgs, t: float, wei
     dev = model.device
     n, T = len(ctxs), LATENT_TILE
     t = float(t)
-    coarse = torch.stack([_f32(torch.as_tensor(c), dev) for c in cond_imgs])                    # [n, 7, 4, 4] packed
+    cond_imgs = [torch.as_tensor(c) for c in cond_imgs]
+    if all(c.device.type == "cpu" for c in cond_imgs):            # host windows (the reference's convention): ONE copy
+        coarse = _f32(torch.stack(cond_imgs), dev)
+    else:
+        coarse = torch.stack([_f32(c, dev) for c in cond_imgs])                                  # [n, 7, 4, 4] packed
     cimg = torch.cat([coarse[:, :-1] / coarse[:, -1:], torch.ones((n, 1, 4, 4), device=dev)], dim=1)
     cvec = process_latent_conditioning(cimg, histogram_raw, cond_means, cond_stds, torch.tensor(0.0))
-    z = torch.stack([gaussian_noise_patch(seed + seed_offset, c[1] * LATENT_STRIDE, c[2] * LATENT_STRIDE, T, T, 5, T, T,
-                                          device=dev) for c in ctxs])
+    z = gaussian_noise_patches(seed + seed_offset, [(c[1] * LATENT_STRIDE, c[2] * LATENT_STRIDE) for c in ctxs], T, T, 5,
+                               T, T, device=dev)
     first = samples is None or all(s is None for s in samples)
     if first:
         x = z                                                   # s = 0: x_t = sin t sigma_d z, folded into the program
