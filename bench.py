@@ -12,7 +12,13 @@ steps inside a solve are data-dependent).  `value` = tile-steps/s over all ranks
 every solve's result.  Weights are seeded synthetic (no checkpoints offline); data is synthetic.
 
 --impl reference times the reference's own algorithm on the host CPU cores (the oracle port, fp32, all threads) --
-rank 0 only, bounded number of steps.
+rank 0 only, bounded number of steps.  --impl reference-gpu: the same algorithm through PyTorch library kernels on the
+GPU (bf16 eager and torch.compile), the stated kernel to beat.
+
+Other workloads (not the driver's line): --workload canvas|export strong-scales ONE blended canvas over the ranks
+(BASELINE configs[2] / configs[3]-shaped); --workload latent = the latent consistency stage (253 M base U-Net, batches of
+64^2 tiles); --workload world = the reference's TTFT / TTST latency harness (evaluation/latency.py)
+through the drop-in WorldPipeline.
 """
 from __future__ import annotations
 
@@ -471,6 +477,96 @@ def run_latent_arm(args, rank, local_rank, world):
         dist.destroy_process_group()
 
 
+# ----------------------------------------------------------------------------------------------------- world arm
+COARSE_CFG = dict(image_size=16, in_channels=11, out_channels=6, model_channels=128, model_channel_mults=[1],
+                  layers_per_block=2, attn_resolutions=[], midblock_attention=False, concat_balance=0.5,
+                  conditional_inputs=[["float", 64, 0.2]] * 5, fourier_scale="pos", block_kwargs={})
+"""configs/diffusion_coarse/diffusion_coarse.cfg:50-62."""
+
+
+def run_world_arm(args, rank, local_rank, world):
+    """The reference's own latency harness (evaluation/latency.py:19-127) through the drop-in `WorldPipeline`: TTFT = the
+    first `get(i, j, i + 512, j + 512)` at a location far from everything computed before (coarse 20-step windows, two
+    latent phases in batches of up to 16, 1-step decoder windows 512 @ stride 384, read-out, D2H); TTST = the adjacent
+    tile.  Synthetic conditioning (no rasters), seeded random weights; plans / graphs are built by the warm-up get as in
+    the reference (its torch.compile warm-up).  Runs on rank 0 only (a latency, not a throughput)."""
+    import random
+    from terrain_diffusion_b200.inference import WorldPipeline
+    from terrain_diffusion_b200.models import EDMUnet2D
+    from oracle import unet as ounet
+    if rank != 0:
+        return
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+
+    def build(cfg):
+        m = EDMUnet2D(**cfg).eval()
+        m.load_state_dict(ounet.procedural_state_dict(cfg, seed=0))
+        return m
+
+    def cond_fn(i1, i2, j1, j2):
+        gg = torch.Generator().manual_seed((i1 * 7919 + j1 + 12345) & 0x7FFFFFFF)
+        return torch.randn(5, i2 - i1, j2 - j1, generator=gg)
+
+    tile = args.size if args.size != 256 else 512
+    pipe = WorldPipeline.from_local_models(build(COARSE_CFG), build(BASE_CFG), build(ounet.DECODER_CFG), seed=42,
+                                           latents_batch_size=[1, 2, 4, 8, 16], torch_compile=True, dtype="bf16",
+                                           caching_strategy="direct", cache_limit=None, decoder_tile_size=512,
+                                           decoder_tile_stride=384, conditioning_fn=cond_fn)
+    pipe.to(dev)
+    pipe.bind("TEMP")
+    torch.cuda.reset_peak_memory_stats()
+    t0 = time.perf_counter()
+    pipe.get(0, 0, tile, tile, with_climate=False)                 # warm-up: plans, graphs, folded weights
+    torch.cuda.synchronize()
+    warm_s = time.perf_counter() - t0
+    sep = 100_000
+    rnd = random.Random(7)
+    for k in range(max(0, args.warmup)):                           # further untimed gets: the other padded batch sizes
+        wi, wj = -(k + 1) * sep + rnd.randint(0, sep // 10), rnd.randint(0, sep)
+        pipe.get(wi, wj, wi + tile, wj + tile, with_climate=False)
+        pipe.empty_cache()
+    torch.cuda.synchronize()
+    ttft, ttst = [], []
+    runs = max(1, args.steps)
+    with ClockSampler(local_rank) as clk:
+        for run in range(runs):
+            bi = (run + 1) * sep + rnd.randint(0, sep // 10)
+            bj = rnd.randint(0, sep)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            pipe.get(bi, bj, bi + tile, bj + tile, with_climate=False)
+            torch.cuda.synchronize()
+            t1 = time.perf_counter()
+            pipe.get(bi, bj + tile, bi + tile, bj + 2 * tile, with_climate=False)
+            torch.cuda.synchronize()
+            t2 = time.perf_counter()
+            ttft.append(t1 - t0)
+            ttst.append(t2 - t1)
+            pipe.empty_cache()
+
+    def pct(v, q):
+        s_ = sorted(v)
+        return s_[int((len(s_) - 1) * q / 100 + 0.5)]
+    mean = sum(ttft) / len(ttft)
+    line = {"metric": "TTFT: seconds to the first 512^2 WorldPipeline.get() at a cold location", "value": mean,
+            "unit": "s", "n_gpus": 1, "steps": runs, "warmup": 1 + max(0, args.warmup), "ms_per_step": mean * 1e3, "higher_is_better": False,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "evaluation/latency.py harness: WorldPipeline (coarse 2.8M / base 253M / decoder 27.9M, "
+                                   "seeded random weights, synthetic conditioning), get() of one 512^2 tile far from "
+                                   "the cache (TTFT) and of its neighbour (TTST), decoder windows 512 @ 384, latent "
+                                   "batches <= 16", "tile": tile, "runs": runs},
+            "ttft": {"mean": mean, "p5": pct(ttft, 5), "p50": pct(ttft, 50), "p95": pct(ttft, 95)},
+            "ttst": {"mean": sum(ttst) / len(ttst), "p5": pct(ttst, 5), "p50": pct(ttst, 50), "p95": pct(ttst, 95)},
+            "first_get_with_plan_building_s": warm_s,
+            "peak_vram_mb": torch.cuda.max_memory_allocated() / 2 ** 20,
+            "clocks": clk.summary(),
+            "e2e": {"value": mean, "unit": "s", "h2d_bytes_per_step": None, "d2h_bytes_per_step": tile * tile * 4,
+                    "api": "terrain_diffusion_b200.inference.WorldPipeline.get"}}
+    print(json.dumps(line), flush=True)
+    pipe.close()
+
+
 # ----------------------------------------------------------------------------------------------------- our arm
 def main():
     ap = argparse.ArgumentParser()
@@ -481,7 +577,7 @@ def main():
     ap.add_argument("--tiles", type=int, default=1, help="independent tiles solved together per GPU")
     ap.add_argument("--size", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="tiles", choices=["tiles", "canvas", "export", "latent"],
+    ap.add_argument("--workload", default="tiles", choices=["tiles", "canvas", "export", "latent", "world"],
                     help="tiles (default, the BASELINE metric: independent 256^2 tiles per GPU, weak scaling) | canvas "
                          "(configs[2]: one 1664^2 canvas, strong scaling) | export (configs[3]-shaped 9344^2 canvas)")
     ap.add_argument("--solve-steps", type=int, default=SOLVE_STEPS, help="denoising steps per tile (canvas workloads)")
@@ -502,6 +598,9 @@ def main():
         return
     if args.workload == "latent":
         run_latent_arm(args, rank, local_rank, world)
+        return
+    if args.workload == "world":
+        run_world_arm(args, rank, local_rank, world)
         return
     if args.workload != "tiles":
         run_canvas_arm(args, rank, local_rank, world)

@@ -27,5 +27,5 @@ def test_gpu_arms_are_declared():
     src = (ROOT / "bench.py").read_text()
     for flag in ("--gpus", "--steps", "--warmup", "--impl", "--tiles", "--size", "--workload"):
         assert flag in src
-    for w in ("tiles", "canvas", "export", "latent"):
+    for w in ("tiles", "canvas", "export", "latent", "world"):
         assert f'"{w}"' in src
