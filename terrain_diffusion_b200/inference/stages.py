@@ -87,12 +87,32 @@ def decoder_stage_tile(model, seed: int, ctx, latents: torch.Tensor, weight_wind
 
 
 # ------------------------------------------------------------------------------------------------ latent stage
+_DEV_CONSTS: dict = {}
+
+
+def _const_on(dev, t) -> torch.Tensor:
+    """fp32 device copy of a small HOST constant (statistics vectors, histogram, noise level), cached by CONTENT: every
+    stage call passes the same few values, and each pageable `.to(device)` is a blocking copy (these copies were half
+    of the host time of a cold `WorldPipeline.get`)."""
+    t = torch.as_tensor(t)
+    if t.device.type != "cpu" or t.numel() > 4096:
+        return t.to(device=dev, dtype=torch.float32)
+    t = t.detach().to(torch.float32).contiguous()
+    key = (str(dev), tuple(t.shape), t.numpy().tobytes())
+    hit = _DEV_CONSTS.get(key)
+    if hit is None:
+        if len(_DEV_CONSTS) > 256:
+            _DEV_CONSTS.clear()
+        hit = _DEV_CONSTS[key] = t.to(dev)
+    return hit
+
+
 def _concat_scales(dims, dev) -> torch.Tensor:
     """mp_concat with equal weights (mp_layers.py:65-86) as ONE per-column scale vector: part i of width N_i is
     multiplied by sqrt(sum N / sum w^2) / sqrt(N_i) * w_i with w_i = 1 / len(parts)."""
     k = len(dims)
     c = math.sqrt(sum(dims) / (k * (1.0 / k) ** 2))
-    return torch.cat([torch.full((d,), c / math.sqrt(d) / k, dtype=torch.float32) for d in dims]).to(dev)
+    return _const_on(dev, torch.cat([torch.full((d,), c / math.sqrt(d) / k, dtype=torch.float32) for d in dims]))
 
 
 @torch.no_grad()
@@ -104,10 +124,11 @@ def process_latent_conditioning(cond_img, histogram_raw, cond_means, cond_stds, 
     compatibility."""
     dev = cond_img.device
     n = cond_img.shape[0]
-    x = (cond_img.float() - cond_means.to(dev).view(1, -1, 1, 1)) / cond_stds.to(dev).view(1, -1, 1, 1)
-    x = torch.nan_to_num(x, nan=float(cond_means[0]))
-    level = ((torch.as_tensor(noise_level, dtype=torch.float32) - 0.5) * math.sqrt(12)).reshape(-1, 1).to(dev)
-    hist = histogram_raw.to(dev).float().reshape(1, -1)
+    cond_means = torch.as_tensor(cond_means)
+    x = (cond_img.float() - _const_on(dev, cond_means).view(1, -1, 1, 1)) / _const_on(dev, cond_stds).view(1, -1, 1, 1)
+    x = torch.nan_to_num(x, nan=float(cond_means.flatten()[0]))
+    level = _const_on(dev, ((torch.as_tensor(noise_level, dtype=torch.float32).cpu() - 0.5) * math.sqrt(12)).reshape(-1, 1))
+    hist = _const_on(dev, histogram_raw).reshape(1, -1)
     parts = [x[:, 0].flatten(1), x[:, 1].flatten(1), x[:, 2:6, 1:3, 1:3].mean(dim=(2, 3)), x[:, 6].flatten(1),
              hist.expand(n, -1), level.expand(n, -1)]
     return torch.cat(parts, dim=1) * _concat_scales([p.shape[1] for p in parts], dev)
@@ -162,16 +183,16 @@ def coarse_stage_tile(model, scheduler, seed: int, ctx, synthetic_map: torch.Ten
     dev = model.device
     T = COARSE_TILE
     y0, x0 = ctx[1] * COARSE_STRIDE, ctx[2] * COARSE_STRIDE
-    means = torch.as_tensor(coarse_means, dtype=torch.float32, device=dev)
-    stds = torch.as_tensor(coarse_stds, dtype=torch.float32, device=dev)
+    means = _const_on(dev, torch.as_tensor(coarse_means, dtype=torch.float32))
+    stds = _const_on(dev, torch.as_tensor(coarse_stds, dtype=torch.float32))
     sel = [0, 2, 3, 4, 5]                                        # model statistics of the map's five channels (:925)
     smap = (_f32(synthetic_map, dev) - means[sel, None, None]) / stds[sel, None, None]
-    tc = t_cond.to(dev, torch.float32).view(-1, 1, 1)
+    tc = _const_on(dev, t_cond).view(-1, 1, 1)
     cond = (torch.cos(tc) * smap + torch.sin(tc) * gaussian_noise_patch(seed, y0, x0, T, T, 5, T, T, device=dev))[None]
     solve = get_diffusion_solve(model, scheduler, 1, T, T, num_steps)
     noise = gaussian_noise_patch(seed + 1, y0, x0, T, T, 6, T, T, device=dev)[None]
     sample = solve.run(noise * float(scheduler.sigmas[0]), cond,
-                       conditional_inputs=[c.to(dev, torch.float32) for c in cond_inputs])
+                       conditional_inputs=[_const_on(dev, c) for c in cond_inputs])
     out = sample / float(scheduler.config.sigma_data) * stds.view(1, -1, 1, 1) + means.view(1, -1, 1, 1)
     out[:, 1] = out[:, 0] - out[:, 1]                            # channel 1 is predicted as (ch0 - ch1) (:953)
     return pack_weighted(out.contiguous(), _f32(weight_window, dev))[0]
