@@ -575,19 +575,55 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CU
     const int col0 = kpart * slice;                       // first accumulator column this CTA finalises
     const int chbase = tw.split * p.ncta + col0;          // first output channel this CTA writes
     const uint32_t plane = (uint32_t)(p.H * p.W);         // (all tensor offsets fit 32 bits: igemm_validate)
-    // uint4 offset of a pixel in an NC8HW8 tensor of this launch's (scaled) geometry, channel group 0
-    auto pixel_off_at = [&](int spatial, int img_, int Y_, int X_) -> uint32_t {
-      if (spatial == TDX_SP_DOWN2)
-        return ((uint32_t)(img_ * C8) * (plane >> 2)) + (uint32_t)((Y_ >> 1) * (p.W >> 1) + (X_ >> 1));
-      if (spatial == TDX_SP_UP2)
-        return ((uint32_t)(img_ * C8) * (plane << 2)) + (uint32_t)((Y_ << 1) * (p.W << 1) + (X_ << 1));
-      return (uint32_t)(img_ * C8) * plane + (uint32_t)(Y_ * p.W + X_);
+    // Element offset of this thread's pixel in a tensor of this launch's (scaled) geometry.  A tile origin (16 ty, 8 tx) is
+    // even, so the offset is SEPARABLE: off = [img * istride + ty * rowstep + tx * colstep] + tpart, where the bracket
+    // is warp-uniform and per item (three multiply-adds from launch constants) and `tpart` is a per-thread constant.
+    // (The former per-item evaluation of (Y >> 1) * (W >> 1) + ..., with its branches on the spatial mode, was most of
+    // the ~500 non-arithmetic instructions an epilogue warp spent per item.)
+    struct OffSpec {
+      uint32_t istride, rowstep, colstep, tpart;
+    };
+    auto make_spec = [&](int spatial, uint32_t planes_per_img) -> OffSpec {
+      OffSpec o;
+      if (spatial == TDX_SP_DOWN2) {
+        o.istride = planes_per_img * (plane >> 2);
+        o.rowstep = (uint32_t)(kTileH / 2) * (uint32_t)(p.W >> 1);
+        o.colstep = kTileW / 2;
+        o.tpart = (uint32_t)((y >> 1) * (p.W >> 1) + (x >> 1));
+      } else if (spatial == TDX_SP_UP2) {
+        o.istride = planes_per_img * (plane << 2);
+        o.rowstep = (uint32_t)(kTileH * 2) * (uint32_t)(p.W << 1);
+        o.colstep = kTileW * 2;
+        o.tpart = (uint32_t)((y << 1) * (p.W << 1) + (x << 1));
+      } else {
+        o.istride = planes_per_img * plane;
+        o.rowstep = (uint32_t)kTileH * (uint32_t)p.W;
+        o.colstep = kTileW;
+        o.tpart = (uint32_t)(y * p.W + x);
+      }
+      return o;
+    };
+    auto item_off = [&](const OffSpec& o, const TileWalk& t) -> uint32_t {
+      return (uint32_t)t.img * o.istride + (uint32_t)t.ty * o.rowstep + (uint32_t)t.tx * o.colstep + o.tpart;
     };
     // Residual reads.  "UP2" = the residual is at half resolution, "DOWN2" = at double resolution (the inverse of an
     // output's meaning).
     const bool has_resid = (p.epi & TDX_EPI_RESID) != 0;
     const uint32_t rplane = p.resid_spatial == TDX_SP_UP2 ? (plane >> 2) : (p.resid_spatial == TDX_SP_DOWN2 ? (plane << 2) : plane);
     const int rsp = p.resid_spatial == TDX_SP_UP2 ? TDX_SP_DOWN2 : (p.resid_spatial == TDX_SP_DOWN2 ? TDX_SP_UP2 : TDX_SP_SAME);
+    const OffSpec rspec = make_spec(rsp, (uint32_t)C8), rinv_spec = make_spec(rsp, 1u);
+    // outputs: the channel-slice offset of this CTA is folded into the thread part; bit o of `omask` = output o exists
+    // and this thread's pixel is stored (an odd pixel of a 2x-downsampled output is not: (Y | X) & 1 == (y | x) & 1)
+    OffSpec ospec[3];
+    uint32_t omask = 0;
+#pragma unroll
+    for (int o = 0; o < 3; ++o) {
+      const int sp = p.out[o].spatial;
+      ospec[o] = make_spec(sp, (uint32_t)C8);
+      const uint32_t oplane = sp == TDX_SP_DOWN2 ? (plane >> 2) : (sp == TDX_SP_UP2 ? (plane << 2) : plane);
+      ospec[o].tpart += (uint32_t)(chbase >> 3) * oplane;
+      if (p.out[o].kind != TDX_OUT_NONE && !(sp == TDX_SP_DOWN2 && ((y | x) & 1)) && !TDX_DBG(16)) omask |= 1u << o;
+    }
     // The values an item needs from global memory before it can touch its accumulator are requested ONE ITEM AHEAD
     // (`fetch_ahead`, called where the current item has consumed them): the residual's first-chunk channels or the
     // modulation vector's first chunk (`pre`) and the residual's pixel-norm factor (`rinv_pre`).  Requested at the start of
@@ -610,14 +646,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CU
       if (!has_resid) return;
       const int Y_ = t.ty * kTileH + y, X_ = t.tx * kTileW + x;
       const bool vld = (Y_ < p.H) && (X_ < p.W);
-      rbase_pre = p.resid + pixel_off_at(rsp, t.img, Y_, X_);
-      if (p.resid_inv) {
-        // the producer of the residual left 1 / (eps + rms) per pixel: one float instead of all Cout channels
-        const uint32_t po = rsp == TDX_SP_DOWN2 ? (uint32_t)t.img * (plane >> 2) + (uint32_t)((Y_ >> 1) * (p.W >> 1) + (X_ >> 1))
-                          : rsp == TDX_SP_UP2 ? (uint32_t)t.img * (plane << 2) + (uint32_t)((Y_ << 1) * (p.W << 1) + (X_ << 1))
-                                              : (uint32_t)t.img * plane + (uint32_t)(Y_ * p.W + X_);
-        rinv_pre = vld ? __ldg(p.resid_inv + po) : 0.f;
-      }
+      rbase_pre = p.resid + item_off(rspec, t);
+      // the producer of the residual left 1 / (eps + rms) per pixel: one float instead of all Cout channels
+      if (p.resid_inv) rinv_pre = vld ? __ldg(p.resid_inv + item_off(rinv_spec, t)) : 0.f;
       const uint4* rptr = rbase_pre + (size_t)((chbase >> 3) + wq * kGroups) * rplane;
 #pragma unroll
       for (int g = 0; g < kGroups; ++g)
@@ -667,8 +698,6 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CU
           for (int j = 0; j < kChunk; ++j) v[j] += __ldcg(src + (size_t)j * 128);
         }
       };
-      // uint4 offset of this thread's pixel in an NC8HW8 tensor of this launch's (scaled) geometry, channel group 0
-      auto pixel_off = [&](int spatial) -> uint32_t { return pixel_off_at(spatial, img, Y, X); };
 
       {
         // ---------------- general: residual mp_sum (+pixel-norm of the residual), clip, pixel-norm, up to 3 outputs
@@ -710,10 +739,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CU
         bool oact[3];
 #pragma unroll
         for (int o = 0; o < 3; ++o) {
-          const int sp = p.out[o].spatial;
-          oact[o] = (p.out[o].kind != TDX_OUT_NONE) && valid && !(sp == TDX_SP_DOWN2 && ((Y | X) & 1)) && !TDX_DBG(16);
-          const uint32_t oplane = sp == TDX_SP_DOWN2 ? (plane >> 2) : (sp == TDX_SP_UP2 ? (plane << 2) : plane);
-          optr[o] = reinterpret_cast<uint4*>(p.out[o].ptr) + pixel_off(sp) + (size_t)(chbase >> 3) * oplane;
+          oact[o] = valid && ((omask >> o) & 1u);
+          optr[o] = reinterpret_cast<uint4*>(p.out[o].ptr) + item_off(ospec[o], tw);
         }
 
         if (warp == 4 && lane == 0) TDX_TRACE(4, it);
