@@ -99,6 +99,39 @@ def test_dependency_windows_use_the_same_window_index_and_batches():
         assert torch.equal(dep, base[:, i - 1:i + 3, j - 1:j + 3])
 
 
+def test_a_request_fills_the_batches_of_its_dependencies():
+    """A canvas that needs several missing windows first makes each dependency compute the UNION of what those windows
+    will read (row-major), so a batched dependency sees full batches instead of one small request per window -- and
+    exactly the windows the per-window reads would have computed, with the same values."""
+    sizes = []
+
+    def f_mid(ctxs):
+        sizes.append(len(ctxs))
+        return [torch.full((1, 8, 8), float(c[1] * 10 + c[2]), device="cuda") for c in ctxs]
+
+    def build(batch):
+        sizes.clear()
+        mid = LazyCanvas(1, f_mid, TensorWindow((1, 8, 8), (1, 4, 4)), "cuda", batch_size=batch)
+        top = LazyCanvas(1, lambda ctx, dep: dep * 2.0, TensorWindow((1, 8, 8), (1, 8, 8)), "cuda", args=(mid,),
+                         args_windows=(TensorWindow((1, 8, 8), (1, 8, 8)),))
+        return mid, top
+
+    mid, top = build(16)
+    out = top[:, 0:32, 0:32]                                   # 4 x 4 top windows, each reads 3 x 3 mid windows
+    assert mid.windows_computed == 9 * 9 == sum(sizes)         # the union: mid windows -1..7 per axis, each ONCE
+    assert sizes[:5] == [16] * 5 and sizes[5] == 1 and len(sizes) == 6
+    one_by_one = LazyCanvas(1, lambda ctx: f_mid([ctx])[0], TensorWindow((1, 8, 8), (1, 4, 4)), "cuda")
+    ref = LazyCanvas(1, lambda ctx, dep: dep * 2.0, TensorWindow((1, 8, 8), (1, 8, 8)), "cuda", args=(one_by_one,),
+                     args_windows=(TensorWindow((1, 8, 8), (1, 8, 8)),))
+    assert torch.equal(out, ref[:, 0:32, 0:32])
+    # a dependency whose cache limit cannot hold the union is left alone: windows are computed on demand as before
+    sizes.clear()
+    small = LazyCanvas(1, f_mid, TensorWindow((1, 8, 8), (1, 4, 4)), "cuda", batch_size=16, cache_limit=20 * 8 * 8 * 4)
+    top2 = LazyCanvas(1, lambda ctx, dep: dep * 2.0, TensorWindow((1, 8, 8), (1, 8, 8)), "cuda", args=(small,),
+                      args_windows=(TensorWindow((1, 8, 8), (1, 8, 8)),))
+    assert torch.equal(top2[:, 0:32, 0:32], out) and max(sizes) <= 9
+
+
 def test_three_stage_pipeline_slice_equals_direct_stage_evaluation():
     def build(cfg):
         m = EDMUnet2D(**cfg).eval()
