@@ -123,6 +123,10 @@ __device__ __forceinline__ void stage_locate(const IgemmParams& p, int s, int& s
 #ifndef TDX_DEBUG_HOOKS
 #define TDX_DEBUG_HOOKS 0
 #endif
+// A/B switches of measured experiments (profiles/r02_epilogue_stalls.txt; set through TDX_NVCC_DEFINES, see build.py):
+//   TDX_V_TWO_KERNELS  launches without clusters use the cluster-free instantiation (0: one kernel for everything)
+//   TDX_V_AHEAD_R / _C residual / modulation vector fetched one item ahead (R: 0 = at the item's start; C: 0 = in place,
+//                      1 = at the item's start, 2 = one item ahead)
 #ifndef TDX_V_TWO_KERNELS
 #define TDX_V_TWO_KERNELS 1
 #endif
@@ -818,10 +822,10 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CU
                 mbar_arrive_cluster(map_to_cta(smem_u32(&x_full[par]), r));
               }
               const uint32_t xph = (it >> 1) & 1;
-              {
-                uint32_t spins = 0;
+              if (!mbar_try_wait_cluster(&x_full[par], xph)) {
+                const long long t0 = clock64();
                 while (!mbar_try_wait_cluster(&x_full[par], xph)) {
-                  if (++spins > TDX_WAIT_SPINS) mbar_timeout(700 + par, xph);
+                  if (clock64() - t0 > TDX_WAIT_LIMIT) mbar_timeout(700 + par, xph);
                 }
               }
               for (uint32_t r = 0; r < (uint32_t)p.xsplit; ++r)

@@ -50,52 +50,26 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a broken pipeline traps (visible as a CUDA error on the host) instead of hanging the GPU box.  The
-// bound is a spin count (a try_wait suspends the thread for a hardware-defined time, ~1 us at most) and the report
-// lives in a function that is never inlined, so a wait site is five instructions in the instruction stream.
 // Bounded wait: a broken pipeline traps (visible as a CUDA error on the host) instead of hanging the GPU box.
-// TDX_V_WAIT selects how the time-out is raised (measured, profiles/r02_epilogue_diet_ab.txt):
-//   0  printf + trap inline in the wait loop
-//   1  a noinline, NORETURN reporter, loop bounded by the clock      2  the same, loop bounded by a poll counter
-// A plain noinline reporter (returning as far as the caller knows) costs 12 % of the whole step: a call that may
-// return clobbers the uniform registers, so the MMA issuer's ring state is spilled / re-converted (R2UR) around every
-// wait.  How often try_wait is re-polled (clock read between polls, suspend-time hint, nanosleep) makes no difference.
-#ifndef TDX_V_WAIT
-#define TDX_V_WAIT 1
-#endif
+// The reporter is out of line and NORETURN.  Declared as an ordinary noinline function (one that may return) the same
+// code cost 12 % of the whole step: a call that may return clobbers the uniform registers, so the MMA issuer's and the
+// producers' ring state was spilled / re-converted (R2UR) around every wait.  How often try_wait is re-polled (clock
+// read between polls, suspend-time hint, nanosleep) makes no difference (profiles/r02_epilogue_diet_ab.txt).
 #ifndef TDX_WAIT_LIMIT
 #define TDX_WAIT_LIMIT (1ll << 31)   // ~1 s of SM clocks
 #endif
-#ifndef TDX_WAIT_SPINS
-#define TDX_WAIT_SPINS (1u << 24)
-#endif
-#if TDX_V_WAIT == 0
-__device__ __forceinline__ void mbar_timeout(int tag, uint32_t parity) {
-  printf("tdx: mbarrier wait timeout tag=%d block=%d thread=%d parity=%u\n", tag, (int)blockIdx.x, (int)threadIdx.x,
-         parity);
-  __trap();
-}
-#else
 static __device__ __noinline__ __attribute__((noreturn)) void mbar_timeout(int tag, uint32_t parity) {
   printf("tdx: mbarrier wait timeout tag=%d block=%d thread=%d parity=%u\n", tag, (int)blockIdx.x, (int)threadIdx.x,
          parity);
   __trap();
   for (;;) {}
 }
-#endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag) {
   if (mbar_try_wait(bar, parity)) return;
-#if TDX_V_WAIT != 2
-  long long t0 = clock64();
+  const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
     if (clock64() - t0 > TDX_WAIT_LIMIT) mbar_timeout(tag, parity);
   }
-#else
-  uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if (++spins > TDX_WAIT_SPINS) mbar_timeout(tag, parity);
-  }
-#endif
 }
 
 // ---------------------------------------------------------------- TMA
