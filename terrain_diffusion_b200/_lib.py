@@ -195,22 +195,40 @@ def check(rc: int) -> None:
         raise TdxError(f"libtdx error {rc}: {lib().tdx_last_error().decode()}")
 
 
+def _raw_stream(index: int) -> int:
+    import torch
+    fast = getattr(torch._C, "_cuda_getCurrentRawStream", None)      # the cudaStream_t itself, no Stream object
+    return int(fast(index)) if fast is not None else torch.cuda.current_stream(index).cuda_stream
+
+
 def current_stream_ptr(device=None) -> int:
     import torch
-    return torch.cuda.current_stream(device).cuda_stream
+    if device is None:
+        return _raw_stream(torch.cuda.current_device())
+    device = torch.device(device)
+    return _raw_stream(device.index if device.index is not None else torch.cuda.current_device())
 
 
 def call(fn, device, *args) -> None:
     """One libtdx launch on `device`: the device is made current for the call (libtdx launches on, and takes its
     per-device scratch / SM count from, the CURRENT device -- it never calls cudaSetDevice itself) and the device's
     current torch stream is appended as the last C argument.  A tensor that lives on cuda:1 while cuda:0 is current
-    would otherwise run on device 0 with device-1 pointers."""
+    would otherwise run on device 0 with device-1 pointers.  (When the device already is current -- the usual case --
+    the call costs one device query and one raw-stream query: a `get()` of the pipeline makes ~900 of them.)"""
     import torch
-    device = torch.device(device)
+    if not isinstance(device, torch.device):
+        device = torch.device(device)
     if device.type != "cuda":
         raise TdxError(f"libtdx launch on a non-CUDA device ({device}); there is no CPU path")
-    with torch.cuda.device(device):
-        check(fn(*args, torch.cuda.current_stream(device).cuda_stream))
+    cur = torch.cuda.current_device()
+    idx = cur if device.index is None else device.index
+    if idx == cur:
+        rc = fn(*args, _raw_stream(idx))
+    else:
+        with torch.cuda.device(idx):
+            rc = fn(*args, _raw_stream(idx))
+    if rc != 0:
+        check(rc)
 
 
 def igemm_choose_n(c_out: int, n_img: int, height: int, width: int, segs) -> int:

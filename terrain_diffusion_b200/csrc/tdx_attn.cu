@@ -100,10 +100,9 @@ int attn_validate(const TdxAttnDesc& d) {
 }
 
 int attn_prepare() {
-  static bool done = false;
-  if (!done) {
+  static bool seen[16] = {false};
+  if (first_use_on_device(seen)) {
     TDX_CHECK_CUDA(cudaFuncSetAttribute(attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    done = true;
   }
   return TDX_OK;
 }

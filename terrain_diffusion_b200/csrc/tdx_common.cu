@@ -29,6 +29,17 @@ int sm_count() {
   return n[dev];
 }
 
+// True the first time it is called for the CURRENT device with this flag set (cudaFuncSetAttribute is per device: a
+// process that drives two GPUs must opt each kernel in to its dynamic shared memory on both).
+bool first_use_on_device(bool (&seen)[16]) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 16) dev = 0;
+  if (seen[dev]) return false;
+  seen[dev] = true;
+  return true;
+}
+
 static bool use_pdl() {
   static int v = -1;
   if (v < 0) {

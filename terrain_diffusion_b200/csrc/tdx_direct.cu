@@ -415,13 +415,12 @@ __global__ void __launch_bounds__(128) conv_out_kernel(const ConvOutParams p) {
 
 // Opt in to > 48 KB dynamic shared memory once (must not happen inside a stream capture).
 int direct_prepare() {
-  static bool done = false;
-  if (!done) {
+  static bool seen[16] = {false};
+  if (first_use_on_device(seen)) {
     TDX_CHECK_CUDA(cudaFuncSetAttribute(conv_in_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     TDX_CHECK_CUDA(cudaFuncSetAttribute(conv_in_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     TDX_CHECK_CUDA(cudaFuncSetAttribute(conv_out_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     TDX_CHECK_CUDA(cudaFuncSetAttribute(conv_out_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    done = true;
   }
   return TDX_OK;
 }

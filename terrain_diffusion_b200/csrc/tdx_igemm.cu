@@ -902,11 +902,10 @@ static int g_dbg_flags = 0;
 static int ensure_scratch(float** ws);
 
 int igemm_prepare() {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool seen[16] = {false};
+  if (first_use_on_device(seen)) {
     TDX_CHECK_CUDA(cudaFuncSetAttribute(igemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
     TDX_CHECK_CUDA(cudaFuncSetAttribute(igemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
-    attr_set = true;
   }
   float* ws;
   return ensure_scratch(&ws);

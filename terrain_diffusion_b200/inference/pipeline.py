@@ -185,7 +185,31 @@ class WorldPipeline:
             from .. import _lib as L
             raise L.TdxError("WorldPipeline (B200 path) needs its models on a CUDA device before bind(); no CPU path")
         self._build_hierarchy()
+        if self.torch_compile:
+            self._prebuild_programs()
         return self
+
+    def _prebuild_programs(self) -> None:
+        """`torch_compile=True` in the reference compiles the models for the configured batch sizes before serving
+        (world_pipeline.py:393-398, 421-430).  The equivalent here: build (fold, plan, capture) the consistency
+        programs of the latent stage for every padded batch size and both phases, and the decoder / coarse programs, so
+        that no `get()` pays a plan build the first time a new batch size turns up (0.3-0.5 s each)."""
+        from .samplers import get_consistency_solve, get_diffusion_solve
+        sd = 0.5
+        if self.base_model is not None:
+            phases = [(self.t_init, True)] + ([] if self.onestep_latent else [(self.t_inter, False)])
+            for m in self._batch_sizes:
+                for t, first in phases:
+                    get_consistency_solve(self.base_model, int(m), 64, 64, float(t), sd, from_unit_noise=first,
+                                          out_scale=1.0 / sd).prog.instantiate()
+        if self.decoder_model is not None:
+            T_ = self.decoder_tile_size
+            get_consistency_solve(self.decoder_model, 1, T_, T_, float(self.t_init), sd, from_unit_noise=True,
+                                  out_scale=1.0 / sd).prog.instantiate()
+        if self.coarse_model is not None:
+            get_diffusion_solve(self.coarse_model, EDMDPMSolverMultistepScheduler(sigma_min=0.002, sigma_max=80,
+                                                                                   sigma_data=0.5), 1, 64, 64,
+                                20).prog.instantiate()
 
     # ------------------------------------------------------------------ conditioning (injected; see module docstring)
     def _set_cond(self, cond_snr) -> None:

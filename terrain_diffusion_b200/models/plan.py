@@ -507,6 +507,11 @@ class UNetEmitter:
 
     # ------------------------------------------------------------------ embedding / modulation vectors
     def emit_embed(self, prog: UNetProgram, labels=None, emb_in=None):
+        # (planning allocates per-device library scratch and asks per-device questions: the model's device is current)
+        with torch.cuda.device(self.dev):
+            return self._emit_embed(prog, labels, emb_in)
+
+    def _emit_embed(self, prog: UNetProgram, labels=None, emb_in=None):
         """One launch producing the modulation vectors c_b of every block for `cvec_sets * n` label rows.
         labels: fp32 [cvec_sets * n] device tensor, or emb_in: fp32 [cvec_sets * n, E] (host-computed embedding)."""
         fw = self.fw
@@ -546,6 +551,10 @@ class UNetEmitter:
 
     # ------------------------------------------------------------------ one U-Net evaluation
     def emit(self, prog: UNetProgram, srcs, model_out=None, sched=None, cvec_set: int = 0):
+        with torch.cuda.device(self.dev):
+            return self._emit(prog, srcs, model_out, sched, cvec_set)
+
+    def _emit(self, prog: UNetProgram, srcs, model_out=None, sched=None, cvec_set: int = 0):
         """srcs: [(tensor NCHW fp32/bf16, channels, scale_ptr_tensor or None)] (1 or 2 sources);
         model_out: fp32 [n, Cout, h, w] or None; sched: None or dict(coef=tensor[4], sample=tensor, x0_prev=tensor);
         cvec_set: which label set's modulation vectors (see emit_embed) this evaluation uses."""
