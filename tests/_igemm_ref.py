@@ -100,7 +100,7 @@ def reference(case: Case, acts, wts, cvec, resid):
     return outs
 
 
-def run_cuda(case: Case, acts, wts, cvec, resid):
+def run_cuda(case: Case, acts, wts, cvec, resid, rms_out=None, resid_inv=None):
     dev = acts[0].device
     a_dev = [to_nc8hw8(a) for a in acts]
     n_item = case.n_item or L.igemm_choose_n(case.cout, case.n, case.h, case.w, case.segs)
@@ -121,7 +121,11 @@ def run_cuda(case: Case, acts, wts, cvec, resid):
     d.cvec = cvec_dev.data_ptr()
     d.resid = r_dev.data_ptr()
     d.resid_spatial = case.resid_spatial
-    d.resid_pnorm = case.resid_pnorm
+    d.resid_pnorm = case.resid_pnorm if resid_inv is None else 0
+    if rms_out is not None:        # fp32 [n, h, w]: 1 / (eps + rms) of the result, for the consumer's residual
+        d.rms_out = rms_out.data_ptr()
+    if resid_inv is not None:      # fp32 plane at the residual's resolution: replaces the recomputed pixel-norm
+        d.resid_inv = resid_inv.data_ptr()
     d.resid_scale = case.resid_scale
     d.clip = case.clip
     bufs = []
@@ -183,4 +187,12 @@ def default_cases() -> list[Case]:
         Case("resident_multi_item_per_cta", [(64, 9)], 64, 3, 128, 128, epi=E),
         Case("clip_active", [(64, 9)], 64, 1, 16, 16, epi=R, clip=0.5),
         Case("clip_no_resid", [(64, 9), (64, 1)], 64, 1, 16, 16, clip=0.3),
+        # ragged images: H, W multiples of 8 but not of the 16 x 8 work-item tile, several images, every spatial mode
+        Case("ragged_24x40_emb", [(64, 9)], 64, 3, 24, 40, epi=E),
+        Case("ragged_40x24_resid_3outs", [(128, 9)], 128, 2, 40, 24, epi=R, resid_pnorm=1,
+             outs=[(L.OUT_RAW, L.SP_SAME, 1.0), (L.OUT_PNORM_SILU, L.SP_DOWN2, 1.0), (L.OUT_SILU, L.SP_UP2, 0.8)]),
+        Case("ragged_56x72_resid_up", [(64, 9)], 64, 2, 56, 72, epi=R, resid_spatial=L.SP_UP2,
+             outs=[(L.OUT_RAW, L.SP_SAME, 1.0), (L.OUT_SILU, L.SP_SAME, 1.1)]),
+        Case("ragged_24x24_resid_down", [(64, 9)], 64, 2, 24, 24, epi=R, resid_spatial=L.SP_DOWN2, resid_pnorm=1,
+             outs=[(L.OUT_RAW, L.SP_SAME, 1.0), (L.OUT_PNORM_SILU, L.SP_SAME, 1.0)]),
     ]

@@ -20,6 +20,33 @@ def test_igemm_case(case):
         assert float((g - r).abs().max()) <= 2 ** -7 * float(r.abs().max()) + 1e-3
 
 
+def test_pixel_norm_side_channel_rms_out_and_resid_inv():
+    """Round 2: a producer leaves 1 / (eps + rms) per pixel (`rms_out`); the consumer that adds pixelnorm(residual)
+    reads that one float (`resid_inv`) instead of every channel of the residual.  Both against the fp32 definition,
+    on same-size, half-size and double-size residuals and a ragged image."""
+    from terrain_diffusion_b200 import _lib as L
+    from tests._igemm_ref import Case
+    dev = torch.device("cuda:0")
+    R = L.EPI_RESID
+    outs = [(L.OUT_RAW, L.SP_SAME, 1.0), (L.OUT_PNORM_SILU, L.SP_SAME, 1.0)]
+    for case in (Case("inv_same", [(64, 9)], 64, 2, 40, 24, epi=R, resid_pnorm=1, outs=outs),
+                 Case("inv_up", [(128, 9)], 128, 1, 32, 32, epi=R, resid_pnorm=1, resid_spatial=L.SP_UP2, outs=outs),
+                 Case("inv_down", [(64, 9)], 64, 2, 24, 24, epi=R, resid_pnorm=1, resid_spatial=L.SP_DOWN2, outs=outs)):
+        acts, wts, cvec, resid = make_inputs(case, dev)
+        refs = reference(case, acts, wts, cvec, resid)
+        inv_plane = (1.0 / (1e-4 + resid.square().mean(dim=1).sqrt())).contiguous()      # [n, hr, wr] fp32
+        rms = torch.full((case.n, case.h, case.w), float("nan"), device=dev)
+        gots = run_cuda(case, acts, wts, cvec, resid, rms_out=rms, resid_inv=inv_plane)
+        for g_, r in zip(gots, refs):
+            assert rel_rms(g_, r.bfloat16().float()) < 2e-3
+        want = 1.0 / (1e-4 + refs[0].square().mean(dim=1).sqrt())
+        assert not torch.isnan(rms).any()
+        assert float(((rms - want) / want).abs().max()) < 2e-3
+        plain = run_cuda(case, acts, wts, cvec, resid)                                    # recomputed pixel-norm path
+        for a, b in zip(plain, gots):
+            assert rel_rms(a, b) < 2e-3
+
+
 def test_igemm_rejects_bad_descriptors():
     import ctypes as C
     from terrain_diffusion_b200 import _lib as L
