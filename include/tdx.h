@@ -6,6 +6,13 @@
  * passed as void*).  All functions return 0 on success or a negative TDX_E_* code; tdx_last_error() returns a
  * human-readable message for the calling thread.  There is no CPU fallback anywhere behind this header.
  *
+ * Devices and streams: the library launches on the CURRENT device (it never calls cudaSetDevice) -- make the device
+ * that owns the pointers current before a call.  Per-device state (split-K scratch, opted-in kernel attributes, SM
+ * count) is created the first time a device is used and must not be created inside a stream capture: call
+ * tdx_program_add_* / tdx_igemm_run once outside a capture first.  The split-K scratch is ONE buffer per device:
+ * launches on the same device must be stream-ordered with respect to each other (the reference drives its models from
+ * one thread and one stream, world_pipeline.py; so does the Python host here).  Not thread-safe per handle.
+ *
  * Each entry point cites the reference interface (xandergos/terrain-diffusion @ 82a0431) it replaces.
  * The reference has no FFI of its own (pure Python); INTEGRATION.md shows the ctypes stub a maintainer would add.
  *
