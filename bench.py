@@ -271,6 +271,64 @@ def run_reference_gpu_arm(args, rank):
     print(json.dumps(line), flush=True)
 
 
+def run_reference_gpu_latent(args, rank):
+    """--impl reference-gpu --workload latent: the latent consistency stage's arithmetic (base U-Net forward on a batch of
+    64^2 tiles + TrigFlow update, world_pipeline.py:1097-1128) through PyTorch library kernels, bf16 eager and
+    torch.compile -- the kernel to beat for SURVEY 8(f)-1."""
+    if rank != 0:
+        return
+    import math
+    from oracle import unet as ounet
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    B = args.tiles if args.tiles > 1 else 16
+    T, sdat = 64, 0.5
+    t0 = math.atan(80.0 / sdat)
+    sd = {k: v.to(dev) for k, v in ounet.procedural_state_dict(BASE_CFG, seed=0).items()}
+    g = torch.Generator().manual_seed(3)
+    z = torch.randn(B, 5, T, T, generator=g).to(dev)
+    cvec = torch.randn(B, 58, generator=g).to(dev).bfloat16()
+    lab = torch.full((B,), t0, device=dev).bfloat16()
+
+    def fwd(x, t, c):
+        return ounet.unet_forward(sd, BASE_CFG, x, t, [c])
+
+    results = {}
+    variants = [("eager_bf16", fwd)]
+    try:
+        variants.append(("compile_bf16", torch.compile(fwd)))
+    except Exception as e:  # pragma: no cover
+        results["compile_bf16"] = {"unavailable": repr(e)[:200]}
+    for name, f in variants:
+        try:
+            def phase():
+                x_t = math.sin(t0) * sdat * z                       # first phase: s = 0
+                pred = -f((x_t / sdat).bfloat16(), lab, cvec).float()
+                return (math.cos(t0) * x_t - math.sin(t0) * sdat * pred) / sdat
+            with torch.no_grad():
+                for _ in range(max(args.warmup, 3)):
+                    phase()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(args.steps):
+                    phase()
+                e1.record()
+                torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+            results[name] = {"value": B * args.steps / (ms / 1e3), "unit": "tile-phases/s", "ms_per_step": ms / args.steps}
+        except Exception as e:  # pragma: no cover
+            results[name] = {"unavailable": repr(e)[:300]}
+    best = max((r["value"] for r in results.values() if "value" in r), default=None)
+    print(json.dumps({"impl": "reference-gpu", "metric": "latent-stage tile-phases/sec, 64^2 latent tiles, base 253M U-Net",
+                      "value": best, "unit": "tile-phases/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+                      "higher_is_better": True, "dtype": "bf16", "data": "synthetic",
+                      "config": {"workload": f"base U-Net, {B} x 64x64 latent tiles, one consistency phase per step -- the "
+                                             "reference algorithm (oracle restatement) through PyTorch library kernels"},
+                      "variants": results, "gpu_launches": 0,
+                      "note": "comparison arm (the kernel to beat), not the product"}), flush=True)
+
+
 # ----------------------------------------------------------------------------------------------------- canvas arm
 CANVASES = {
     # BASELINE configs[2]: 4 x 4 = 16 overlapping 512-px tiles at stride 384 (training/evaluation/__init__.py:16-22 gives
@@ -594,7 +652,10 @@ def main():
         run_reference_arm(args, rank)
         return
     if args.impl == "reference-gpu":
-        run_reference_gpu_arm(args, rank)
+        if args.workload == "latent":
+            run_reference_gpu_latent(args, rank)
+        else:
+            run_reference_gpu_arm(args, rank)
         return
     if args.workload == "latent":
         run_latent_arm(args, rank, local_rank, world)
