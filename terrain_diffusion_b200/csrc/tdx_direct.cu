@@ -364,6 +364,35 @@ __global__ void __launch_bounds__(128) conv_out_kernel(const ConvOutParams p) {
     float acc[COUT];
 #pragma unroll
     for (int j = 0; j < COUT; ++j) acc[j] = 0.f;
+    if (COUT == 1 && p.C8 == 8) {
+      // the decoder's 64 -> 1 case: all 18 loads of a thread are issued before the first is used (the generic loop
+      // below walks taps and groups with data-dependent control flow: one L2 latency after the other).  Out-of-image
+      // taps contribute exact zeros, so the sum is bit-identical to the generic path.
+      uint4 u[9][2];
+      const uint4* base = p.x + (size_t)img * p.C8 * plane;
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) {
+        const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
+        const bool ok = inb && yy >= 0 && yy < p.H && xx >= 0 && xx < p.W;
+        const uint4* src = base + (ok ? (size_t)yy * p.W + xx : 0);
+        u[tap][0] = ok ? __ldg(src + (size_t)sub * plane) : make_uint4(0, 0, 0, 0);
+        u[tap][1] = ok ? __ldg(src + (size_t)(sub + 4) * plane) : make_uint4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          float a[8];
+          unpack_bf16x2(u[tap][j].x, a[0], a[1]); unpack_bf16x2(u[tap][j].y, a[2], a[3]);
+          unpack_bf16x2(u[tap][j].z, a[4], a[5]); unpack_bf16x2(u[tap][j].w, a[6], a[7]);
+          const float* w = ws + (tap * C + (sub + 4 * j) * 8);
+          const float4 wa = *reinterpret_cast<const float4*>(w), wb = *reinterpret_cast<const float4*>(w + 4);
+          const float t0 = fmaf(wa.x, a[0], wa.y * a[1]), t1 = fmaf(wa.z, a[2], wa.w * a[3]);
+          const float t2 = fmaf(wb.x, a[4], wb.y * a[5]), t3 = fmaf(wb.z, a[6], wb.w * a[7]);
+          acc[0] += (t0 + t1) + (t2 + t3);
+        }
+      }
+    } else
 #pragma unroll
     for (int tap = 0; tap < 9; ++tap) {
       const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
