@@ -731,24 +731,29 @@ def main():
     launches = sum(solves[n].launches_per_solve for n in plan)
 
     # ---------------- e2e: public API, pinned-host inputs, D2H result every solve
-    n_solves = max(1, min(len(plan), 5))
+    n_solves = max(5, min(len(plan), 10))
     out_h = torch.empty(B, 1, S, S).pin_memory()
     sample_decoder_diffusion_tiled(model, sched, cond_d, noise_d, S, S, num_steps=SOLVE_STEPS)  # warm
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    t0 = time.perf_counter()
+    per_solve = []
     for _ in range(n_solves):
+        t0 = time.perf_counter()
         nz = noise_h.to(dev, non_blocking=True)
         cd = cond_h.to(dev, non_blocking=True)
         y = sample_decoder_diffusion_tiled(model, sched, cd, nz, S, S, num_steps=SOLVE_STEPS)
         out_h.copy_(y, non_blocking=True)
         torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    t_e = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        per_solve.append(time.perf_counter() - t0)
+    # the MEDIAN solve (host jitter of a shared box moves the mean by up to 10 %; the mean is reported beside it)
+    e2e_s = sorted(per_solve)[len(per_solve) // 2]
+    e2e_mean_s = sum(per_solve) / len(per_solve)
+    t_e = torch.tensor([e2e_s, e2e_mean_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * n_solves * SOLVE_STEPS / float(t_e.item())
+    e2e_value = world * B * SOLVE_STEPS / float(t_e[0].item())
+    e2e_mean_value = world * B * SOLVE_STEPS / float(t_e[1].item())
     h2d = (noise_h.numel() + cond_h.numel()) * 4 / SOLVE_STEPS
     d2h = out_h.numel() * 4 / SOLVE_STEPS
 
@@ -819,7 +824,9 @@ def main():
                        "gflop_per_tile_step": GFLOP_PER_STEP_256 * (S / 256.0) ** 2},
             "clocks": clk.summary(),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "solves": n_solves, "api": "terrain_diffusion_b200.inference.sample_decoder_diffusion_tiled"},
+                    "solves": n_solves, "stat": "median solve (each solve timed from H2D to the synchronised D2H)",
+                    "value_from_mean": e2e_mean_value,
+                    "api": "terrain_diffusion_b200.inference.sample_decoder_diffusion_tiled"},
             "gpu_launches": launches,
             "roofline": roof,
             "cpu_baseline": cpu_base,
