@@ -103,7 +103,7 @@ def _const_on(dev, t) -> torch.Tensor:
     if hit is None:
         if len(_DEV_CONSTS) > 256:
             _DEV_CONSTS.clear()
-        hit = _DEV_CONSTS[key] = t.to(dev)
+        hit = _DEV_CONSTS[key] = t.clone().to(dev)      # (clone: on a CPU `dev` .to() would alias the caller's tensor)
     return hit
 
 

@@ -211,3 +211,38 @@ def test_integration_md_ctypes_stub_matches_the_library_abi(tmp_path):
     body = header[header.index("typedef struct TdxIgemmDesc {"):header.index("} TdxIgemmDesc;")]
     for name in doc_fields:
         assert re.search(r"\b" + re.escape(name) + r"\b", body), name
+
+
+def test_blend_window_cache_and_device_constant_cache():
+    """Round 2 host-side caches: the blend window is computed once per (size, device, dtype) and equals the reference
+    formula (world_pipeline.py:117-124); small host constants of the stage functions are cached by CONTENT."""
+    from terrain_diffusion_b200.inference import stages
+    from terrain_diffusion_b200.inference.tiling import linear_weight_window
+    w1, w2 = linear_weight_window(64), linear_weight_window(64, "cpu", torch.float32)
+    assert w1 is w2 and w1.shape == (64, 64)
+    mid = 31.5
+    y = torch.arange(64).float()
+    wy = 1 - (1 - 1e-3) * torch.clamp((y - mid).abs() / mid, 0, 1)
+    assert torch.equal(w1, wy[:, None] * wy[None, :])
+    assert linear_weight_window(32) is not w1 and float(w1.min()) > 0
+    a = torch.tensor([1.0, 2.0, 3.0])
+    c1 = stages._const_on(torch.device("cpu"), a)
+    c2 = stages._const_on(torch.device("cpu"), a.clone())           # another object, the same content: the same entry
+    c3 = stages._const_on(torch.device("cpu"), torch.tensor([1.0, 2.0, 4.0]))
+    assert c1 is c2 and c3 is not c1 and torch.equal(c3, torch.tensor([1.0, 2.0, 4.0]))
+    a[0] = 9.0                                                      # mutating the source later does not poison the cache
+    assert float(stages._const_on(torch.device("cpu"), torch.tensor([1.0, 2.0, 3.0]))[0]) == 1.0
+    s = stages._concat_scales([16, 16, 4, 16, 5, 1], torch.device("cpu"))
+    assert s.shape == (58,) and abs(float((s[:16] ** 2).sum() * 6) - 58.0 / 6 * 6) < 1e-3
+
+
+def test_batched_noise_entry_point_validates_without_a_gpu():
+    import ctypes as C
+    lib = L.lib()
+    ys, xs = (C.c_int64 * 2)(0, 32), (C.c_int64 * 2)(0, 32)
+    assert lib.tdx_noise_patches(1, 2, ys, xs, 64, 64, 5, 64, 64, None, None, 0, None) == -1
+    assert b"null" in lib.tdx_last_error()
+    need = lib.tdx_noise_patches_workspace_bytes(5, 64, 64)
+    assert need >= 32 * lib.tdx_noise_patch_workspace_bytes(5, 64, 64) - 32 * 256
+    assert lib.tdx_noise_patches(1, 2, ys, xs, 64, 64, 5, 64, 64, C.c_void_p(16), C.c_void_p(16), 8, None) == -1
+    assert b"workspace" in lib.tdx_last_error()
