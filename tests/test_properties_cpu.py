@@ -76,3 +76,22 @@ def test_phase_split_is_an_ordered_partition_of_the_schedule(num_steps, threshol
     spans = phase_step_ranges(sched, num_steps, thresholds)
     assert spans[0][0] == 0 and spans[-1][1] == num_steps
     assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+
+
+@FAST
+@given(st.integers(2, 60), st.floats(0.001, 0.05), st.floats(5.0, 200.0), st.floats(0.25, 1.0))
+def test_scheduler_tables_and_step_coefficients_match_the_oracle_closed_form(n, smin, smax, sdata):
+    """Sigma table (Karras, rho = 7; dpmsolver.py:329-342) and the per-step update coefficients (Appendix B) of the
+    product scheduler against the oracle's fp64 closed form, for arbitrary step counts and sigma ranges."""
+    from oracle import scheduler as osched
+    s = EDMDPMSolverMultistepScheduler(sigma_min=smin, sigma_max=smax, sigma_data=sdata)
+    s.set_timesteps(n)
+    want = osched.karras_sigmas(n, smin, smax)
+    assert torch.allclose(s.sigmas[:-1].double(), want.double()[:n], rtol=2e-6, atol=0) and float(s.sigmas[-1]) == 0.0
+    ref = osched.step_coefficients(s.sigmas.double(), sdata)
+    order = s.order_schedule()
+    assert order[0] is False and order[-1] is False and all(order[1:-1])      # first / last step first order
+    for i in (0, n // 2, n - 1):
+        co = s.step_coefficients(i, order[i])
+        for key in ("c_in", "t", "c_skip", "c_out", "r", "k"):
+            assert abs(float(co[key]) - ref[i][key]) <= 2e-6 * max(1.0, abs(ref[i][key])), (i, key)
