@@ -29,7 +29,7 @@ if os.environ.get("TDX_DEBUG_HOOKS") == "1":      # ablation flags / trace clock
     NVCC_FLAGS.append("-DTDX_DEBUG_HOOKS=1")
 
 
-for _flag in os.environ.get("TDX_NVCC_DEFINES", "").split():     # A/B experiments: TDX_NVCC_DEFINES="TDX_V_GUARD=0 ..."
+for _flag in os.environ.get("TDX_NVCC_DEFINES", "").split():     # A/B experiments: TDX_NVCC_DEFINES="TDX_V_AHEAD_R=0 TDX_EPI_WQ=4 ..."
     NVCC_FLAGS.append("-D" + _flag)
 
 
