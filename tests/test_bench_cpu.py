@@ -29,3 +29,18 @@ def test_gpu_arms_are_declared():
         assert flag in src
     for w in ("tiles", "canvas", "export", "latent", "world"):
         assert f'"{w}"' in src
+
+
+def test_committed_headline_line_carries_every_contract_key():
+    """The bench line kept under profiles/ (the closing run of the round) has the keys the driver's contract names."""
+    d = json.loads((ROOT / "profiles" / "r02_bench_tiles1.json").read_text())
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline"):
+        assert k in d, k
+    assert d["n_gpus"] == 1 and d["unit"] == "tile-steps/s" and d["dtype"] == "bf16" and d["vs_baseline"] is None
+    r = d["roofline"]
+    assert r["bound"] == "tensor" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and r["traffic"] > 0
+    assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0 and d["e2e"]["value"] < d["value"] * 1.01
+    assert d["cpu_baseline"]["kind"] == "port" and d["gpu_launches"] > 0
+    assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    assert "workload" in d["config"] and "l2" in d["config"]
